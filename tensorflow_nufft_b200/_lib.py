@@ -1,0 +1,218 @@
+"""ctypes binding of libb200nufft.so (C ABI: include/b200nufft.h).
+
+There is NO fallback: if the shared library is missing, or no CUDA device is present, every
+entry point raises. Build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C tensorflow_nufft_b200/csrc`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200nufft.so")
+
+OK, INVALID_ARGUMENT, UNIMPLEMENTED, RESOURCE_EXHAUSTED, INTERNAL = range(5)
+COMPLEX64, COMPLEX128 = 0, 1
+
+
+class Opts(ctypes.Structure):
+  _fields_ = [
+      ("points_range", ctypes.c_int),
+      ("check_points_range", ctypes.c_int),
+      ("max_batch_size", ctypes.c_int),
+      ("spread_only", ctypes.c_int),
+      ("fseries_mode", ctypes.c_int),
+      ("num_threads_compat", ctypes.c_int),
+      ("bin_dims", ctypes.c_int * 3),
+      ("max_subproblem_size", ctypes.c_int),
+      ("spread_method", ctypes.c_int),
+      ("interp_method", ctypes.c_int),
+      ("profile", ctypes.c_int),
+      ("reserved", ctypes.c_int * 8),
+  ]
+
+
+class Info(ctypes.Structure):
+  _fields_ = [
+      ("kernel_width", ctypes.c_int),
+      ("kernel_beta", ctypes.c_double),
+      ("kernel_c", ctypes.c_double),
+      ("upsampling_factor", ctypes.c_double),
+      ("kernel_scale", ctypes.c_double),
+      ("fine_dims", ctypes.c_int * 3),
+      ("bin_dims", ctypes.c_int * 3),
+      ("num_bins", ctypes.c_int * 3),
+      ("batch_size", ctypes.c_int),
+      ("num_threads_compat", ctypes.c_int),
+      ("num_points", ctypes.c_int64),
+      ("subproblem_bound", ctypes.c_int64),
+  ]
+
+
+class NufftError(RuntimeError):
+  """Engine error; `.code` is the C ABI return code."""
+
+  def __init__(self, code, message):
+    super().__init__(message)
+    self.code = code
+
+
+class InvalidArgumentError(NufftError, ValueError):
+  pass
+
+
+_lib = None
+
+# (name, restype, argtypes) for every symbol include/b200nufft.h declares.
+_P = ctypes.c_void_p
+SIGNATURES = [
+    ("b200nufft_default_opts", None, [ctypes.POINTER(Opts)]),
+    ("b200nufft_plan_create", ctypes.c_int,
+     [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+      ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Opts), ctypes.c_int]),
+    ("b200nufft_plan_destroy", None, [_P]),
+    ("b200nufft_set_points", ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P, _P]),
+    ("b200nufft_set_points_interleaved", ctypes.c_int, [_P, ctypes.c_int64, _P, _P]),
+    ("b200nufft_execute", ctypes.c_int, [_P, _P, _P, _P]),
+    ("b200nufft_interp", ctypes.c_int, [_P, _P, _P, _P]),
+    ("b200nufft_spread", ctypes.c_int, [_P, _P, _P, _P]),
+    ("b200nufft_get_sort", ctypes.c_int,
+     [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32)]),
+    ("b200nufft_binsort", ctypes.c_int,
+     [ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, _P, ctypes.POINTER(ctypes.c_int),
+      ctypes.POINTER(ctypes.c_int), ctypes.c_int, _P, _P, _P, _P]),
+    ("b200nufft_fold_rescale", ctypes.c_int,
+     [ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, ctypes.c_int, _P]),
+    ("b200nufft_get_info", ctypes.c_int, [_P, ctypes.POINTER(Info)]),
+    ("b200nufft_get_fseries", ctypes.c_int, [_P, ctypes.c_int, _P]),
+    ("b200nufft_get_timings", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
+    ("b200nufft_launch_count", ctypes.c_int64, [_P]),
+    ("b200nufft_last_error", ctypes.c_char_p, [_P]),
+    ("b200nufft_last_create_error", ctypes.c_char_p, []),
+    ("b200nufft_host_kernel_width", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double]),
+    ("b200nufft_host_next_smooth_int", ctypes.c_int, [ctypes.c_int]),
+    ("b200nufft_host_fseries", ctypes.c_int,
+     [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    ("b200nufft_host_scale_factor", ctypes.c_double, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    ("b200nufft_host_gauss_legendre", ctypes.c_int,
+     [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    ("b200nufft_version", ctypes.c_char_p, []),
+]
+
+
+def lib():
+  """Loads the shared library (once). Raises if it has not been built: no fallback."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(
+          f"{LIB_PATH} is missing: the CUDA engine has not been built and there is no CPU "
+          "fallback. Run `make -C tensorflow_nufft_b200/csrc`.")
+    L = ctypes.CDLL(LIB_PATH)
+    for name, restype, argtypes in SIGNATURES:
+      fn = getattr(L, name)
+      fn.restype = restype
+      fn.argtypes = argtypes
+    _lib = L
+  return _lib
+
+
+def raise_for(code, message):
+  if code == OK:
+    return
+  if code == INVALID_ARGUMENT:
+    raise InvalidArgumentError(code, message)
+  if code == UNIMPLEMENTED:
+    raise NufftError(code, "Unimplemented: " + message)
+  if code == RESOURCE_EXHAUSTED:
+    raise NufftError(code, "ResourceExhausted: " + message)
+  raise NufftError(code, "Internal: " + message)
+
+
+class Plan:
+  """Owns one b200nufft_plan handle. Pointers are raw device addresses (ints)."""
+
+  def __init__(self, transform_type, grid_dims, fft_sign, num_transforms, tol, dtype_code,
+               device=0, **opt_kwargs):
+    L = lib()
+    opts = Opts()
+    L.b200nufft_default_opts(ctypes.byref(opts))
+    for k, v in opt_kwargs.items():
+      if k == "bin_dims":
+        for i, b in enumerate(v):
+          opts.bin_dims[i] = int(b)
+      else:
+        if not hasattr(opts, k):
+          raise TypeError(f"unknown option {k}")
+        setattr(opts, k, int(v))
+    self.rank = len(grid_dims)
+    gd = (ctypes.c_int64 * 3)(*([int(g) for g in grid_dims] + [1] * (3 - self.rank)))
+    h = _P()
+    rc = L.b200nufft_plan_create(ctypes.byref(h), int(transform_type), self.rank, gd, int(fft_sign),
+                                 int(num_transforms), float(tol), int(dtype_code),
+                                 ctypes.byref(opts), int(device))
+    if rc != OK:
+      raise_for(rc, L.b200nufft_last_create_error().decode())
+    self._h = h
+    self.type = int(transform_type)
+    self.num_transforms = int(num_transforms)
+    self.grid_dims = [int(g) for g in grid_dims]
+    self.dtype_code = int(dtype_code)
+    self.device = int(device)
+    self.points_token = None
+
+  def _check(self, rc):
+    if rc != OK:
+      raise_for(rc, lib().b200nufft_last_error(self._h).decode())
+
+  def set_points(self, num_points, x, y, z, stream):
+    self._check(lib().b200nufft_set_points(self._h, int(num_points), x, y, z, stream))
+
+  def set_points_interleaved(self, num_points, pts, stream):
+    self._check(lib().b200nufft_set_points_interleaved(self._h, int(num_points), pts, stream))
+
+  def execute(self, c, f, stream):
+    self._check(lib().b200nufft_execute(self._h, c, f, stream))
+
+  def interp(self, c, f, stream):
+    self._check(lib().b200nufft_interp(self._h, c, f, stream))
+
+  def spread(self, c, f, stream):
+    self._check(lib().b200nufft_spread(self._h, c, f, stream))
+
+  def info(self):
+    inf = Info()
+    self._check(lib().b200nufft_get_info(self._h, ctypes.byref(inf)))
+    return inf
+
+  def sort_pointers(self):
+    idx, bs, bz = _P(), _P(), _P()
+    n = ctypes.c_int32()
+    self._check(lib().b200nufft_get_sort(self._h, ctypes.byref(idx), ctypes.byref(bs),
+                                         ctypes.byref(bz), ctypes.byref(n)))
+    return idx.value, bs.value, bz.value, n.value
+
+  def fseries(self, dim, real_np_dtype):
+    import numpy as np
+    nf = self.info().fine_dims[dim]
+    out = np.empty(nf // 2 + 1, real_np_dtype)
+    self._check(lib().b200nufft_get_fseries(self._h, dim, out.ctypes.data))
+    return out
+
+  def timings(self):
+    out = (ctypes.c_float * 4)()
+    self._check(lib().b200nufft_get_timings(self._h, out))
+    return {"spread_interp_ms": out[0], "fft_ms": out[1], "deconv_ms": out[2], "set_points_ms": out[3]}
+
+  def launch_count(self):
+    return int(lib().b200nufft_launch_count(self._h))
+
+  def close(self):
+    if getattr(self, "_h", None):
+      lib().b200nufft_plan_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass

@@ -1,0 +1,111 @@
+// deconv.cuh -- fused deconvolve+crop (type-1 step 3) and amplify+zero-pad (type-2 step 1).
+// Behavioural reference: Deconvolve{1,2,3}DKernel / Amplify{1,2,3}DKernel nufft_plan.cu.cc:326-435,
+// CPU deconvolve_{1,2,3}d nufft_plan.cc:729-881 (CMCL mode order: index i <-> k = i - N/2; fine
+// index w = k >= 0 ? k : nf + k; factor prod_d phihat_d[|k_d|]; no 1/N anywhere).
+// The arithmetic follows the CPU plan's association ((1/p3)/p2 * v) / p1 so that the parity
+// oracle's roundings are reproduced.
+#pragma once
+#include "dev_common.cuh"
+
+namespace b200 {
+
+struct ModeGeom {
+  int rank;
+  int n[3];    // modes per dim
+  int nf[3];   // fine size per dim
+  int64_t ntot, nftot;
+};
+
+// grid: (ceil(N/256), ntr). fk[t][N] = fw[t][wrap(k)] / factor
+template <typename F>
+__global__ void __launch_bounds__(256)
+deconvolve_kernel(ModeGeom m, const F* __restrict__ p1, const F* __restrict__ p2, const F* __restrict__ p3,
+                  const Cplx<F>* __restrict__ fw, Cplx<F>* __restrict__ fk) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m.ntot) return;
+  const int t = blockIdx.y;
+  const int i1 = static_cast<int>(i % m.n[0]);
+  const int64_t r = i / m.n[0];
+  const int i2 = m.rank > 1 ? static_cast<int>(r % m.n[1]) : 0;
+  const int i3 = m.rank > 2 ? static_cast<int>(r / m.n[1]) : 0;
+  const int k1 = i1 - m.n[0] / 2;
+  const int w1 = k1 >= 0 ? k1 : m.nf[0] + k1;
+  F pre = F(1);
+  int64_t in = w1;
+  if (m.rank > 2) {
+    const int k3 = i3 - m.n[2] / 2;
+    const int w3 = k3 >= 0 ? k3 : m.nf[2] + k3;
+    pre = pre / p3[abs(k3)];
+    in += static_cast<int64_t>(w3) * m.nf[0] * m.nf[1];
+  }
+  if (m.rank > 1) {
+    const int k2 = i2 - m.n[1] / 2;
+    const int w2 = k2 >= 0 ? k2 : m.nf[1] + k2;
+    pre = pre / p2[abs(k2)];
+    in += static_cast<int64_t>(w2) * m.nf[0];
+  }
+  const F f1 = p1[abs(k1)];
+  const Cplx<F> v = fw[static_cast<int64_t>(t) * m.nftot + in];
+  fk[static_cast<int64_t>(t) * m.ntot + i] = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+}
+
+// grid: (ceil(nftot/256), ntr). Writes EVERY fine cell: amplified mode or zero (no memset pass).
+template <typename F>
+__global__ void __launch_bounds__(256)
+amplify_kernel(ModeGeom m, const F* __restrict__ p1, const F* __restrict__ p2, const F* __restrict__ p3,
+               const Cplx<F>* __restrict__ fk, Cplx<F>* __restrict__ fw) {
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= m.nftot) return;
+  const int t = blockIdx.y;
+  const int w1 = static_cast<int>(w % m.nf[0]);
+  const int64_t r = w / m.nf[0];
+  const int w2 = m.rank > 1 ? static_cast<int>(r % m.nf[1]) : 0;
+  const int w3 = m.rank > 2 ? static_cast<int>(r / m.nf[1]) : 0;
+  // mode k_d present iff w_d <= kmax_d (k = w) or w_d >= nf_d + kmin_d (k = w - nf)
+  bool ok = true;
+  int k1, k2 = 0, k3 = 0;
+  {
+    const int kmax = (m.n[0] - 1) / 2, kmin = -(m.n[0] / 2);
+    k1 = w1 <= kmax ? w1 : w1 - m.nf[0];
+    ok = ok && (w1 <= kmax || w1 >= m.nf[0] + kmin);
+  }
+  if (m.rank > 1) {
+    const int kmax = (m.n[1] - 1) / 2, kmin = -(m.n[1] / 2);
+    k2 = w2 <= kmax ? w2 : w2 - m.nf[1];
+    ok = ok && (w2 <= kmax || w2 >= m.nf[1] + kmin);
+  }
+  if (m.rank > 2) {
+    const int kmax = (m.n[2] - 1) / 2, kmin = -(m.n[2] / 2);
+    k3 = w3 <= kmax ? w3 : w3 - m.nf[2];
+    ok = ok && (w3 <= kmax || w3 >= m.nf[2] + kmin);
+  }
+  Cplx<F> out = make_cplx<F>(F(0), F(0));
+  if (ok) {
+    F pre = F(1);
+    int64_t i = k1 + m.n[0] / 2;
+    if (m.rank > 2) {
+      pre = pre / p3[abs(k3)];
+      i += static_cast<int64_t>(k3 + m.n[2] / 2) * m.n[0] * m.n[1];
+    }
+    if (m.rank > 1) {
+      pre = pre / p2[abs(k2)];
+      i += static_cast<int64_t>(k2 + m.n[1] / 2) * m.n[0];
+    }
+    const F f1 = p1[abs(k1)];
+    const Cplx<F> v = fk[static_cast<int64_t>(t) * m.ntot + i];
+    out = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+  }
+  fw[static_cast<int64_t>(t) * m.nftot + w] = out;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+scale_kernel(int64_t n, F s, Cplx<F>* __restrict__ a) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    a[i].x *= s;
+    a[i].y *= s;
+  }
+}
+
+}  // namespace b200

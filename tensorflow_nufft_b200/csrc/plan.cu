@@ -1,0 +1,778 @@
+// plan.cu -- the plan object and the C ABI (include/b200nufft.h) of the B200 NUFFT engine.
+// Orchestration follows the stages of Plan<GPUDevice,F> (nufft_plan.cu.cc:1808-2168) but not its
+// structure: everything is stream-ordered, the cuFFT plan and all buffers live in the plan (so a
+// cached plan costs nothing per call), no host synchronisation in set_points / execute, the
+// stencil records are precomputed once per point set and reused by every transform and execute.
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200nufft.h"
+#include "deconv.cuh"
+#include "dev_common.cuh"
+#include "host_params.h"
+#include "interp.cuh"
+#include "points.cuh"
+#include "scan_sort.cuh"
+#include "spread.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct b200nufft_plan {
+  int type = 0, rank = 0, fft_sign = -1, ntransf = 1, dtype = 0, device = 0;
+  bool is_double = false;
+  b200nufft_opts opts{};
+  KernelParams kp;
+  double tol = 0;
+  double kernel_scale = 0;
+  int64_t n_modes[3] = {1, 1, 1};
+  int64_t n_modes_tot = 1;
+  int nf[3] = {1, 1, 1};
+  int64_t nftot = 1;
+  int batch = 1;
+  int bin[3] = {1, 1, 1};
+  int nbins[3] = {1, 1, 1};
+  int nbtot = 1;
+  int msub = 1024;
+  int PX = 8, PY = 8, R = 8;
+  int num_threads_compat = 1;
+  int spread_method = 1, interp_method = 1;
+  size_t tile_smem = 0;
+
+  // device state
+  DevBuf fine;            // [batch][nftot] complex
+  DevBuf fser[3];         // deconvolution factors
+  std::vector<char> fser_host[3];
+  cufftHandle fft = 0, fft_rem = 0;
+  bool has_fft = false, has_fft_rem = false;
+  int fft_rem_batch = 0;
+
+  int64_t M = 0;
+  bool points_set = false;
+  DevBuf folded[3], keys0, keys1, vals0, vals1, hist, start, wrec;
+  DevBuf bin_sizes, bin_start, num_sub, sub_start, misc;  // misc: scan tmp[1024] + sub_total + range flag
+  int* idx = nullptr;      // points at vals0 or vals1
+  int64_t sub_bound = 0;
+  int* h_flag = nullptr;   // pinned
+
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_exec = false, ev_setpts = false;
+  int64_t launches = 0;
+  char err[768] = {0};
+
+  int* scan_tmp() const { return misc.as<int>(); }
+  int* sub_total() const { return misc.as<int>() + kScanMaxBlocks; }
+  int* range_flag() const { return misc.as<int>() + kScanMaxBlocks + 1; }
+};
+
+namespace {
+
+int set_err(b200nufft_plan* p, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(p->err, sizeof(p->err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(plan, expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return set_err(plan, _e == cudaErrorMemoryAllocation ? B200NUFFT_RESOURCE_EXHAUSTED      \
+                                                           : B200NUFFT_INTERNAL,               \
+                     "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__);    \
+  } while (0)
+
+#define LAUNCH_OK(plan)                                                                        \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return set_err(plan, B200NUFFT_INTERNAL, "kernel launch failed: %s at %s:%d",            \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                              \
+  } while (0)
+
+int grid_for(int64_t n, int threads, int per_sm = 8) {
+  int64_t blocks = (n + threads - 1) / threads;
+  int64_t cap = static_cast<int64_t>(kNumSMsB200) * per_sm;
+  return static_cast<int>(std::max<int64_t>(1, std::min(blocks, cap)));
+}
+
+int ilog2_ceil(int64_t n) {
+  int b = 0;
+  while ((int64_t(1) << b) < n) ++b;
+  return b;
+}
+
+GridGeom grid_geom(const b200nufft_plan* p) {
+  GridGeom g;
+  g.rank = p->rank;
+  for (int d = 0; d < 3; ++d) { g.nf[d] = p->nf[d]; g.bin[d] = p->bin[d]; g.nbins[d] = p->nbins[d]; }
+  g.nftot = p->nftot;
+  return g;
+}
+
+ModeGeom mode_geom(const b200nufft_plan* p) {
+  ModeGeom m;
+  m.rank = p->rank;
+  for (int d = 0; d < 3; ++d) { m.n[d] = static_cast<int>(p->n_modes[d]); m.nf[d] = p->nf[d]; }
+  m.ntot = p->n_modes_tot;
+  m.nftot = p->nftot;
+  return m;
+}
+
+template <typename F>
+void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
+  // PlanBase::points_upper_bound (nufft_plan.h:957-996), RADIANS_PER_SAMPLE
+  F ub = MathConst<F>::pi;
+  if (p->opts.points_range == B200NUFFT_RANGE_EXTENDED) ub *= F(3.0);
+  if (p->opts.points_range == B200NUFFT_RANGE_INFINITE) ub = INFINITY;
+  *hi = ub;
+  *lo = -ub;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile-kernel dispatch on the kernel width.
+// ------------------------------------------------------------------------------------------
+template <int RANK>
+cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+#define SPREAD_CASE(NS)                                                                          \
+  case NS: {                                                                                     \
+    auto k = spread_tile_f32_kernel<NS, RANK>;                                                   \
+    if (p->tile_smem > 48 * 1024)                                                                \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);   \
+    k<<<grid, 32, p->tile_smem, st>>>(p->M, g, p->msub, p->sub_total(), p->sub_start.as<int>(),  \
+                                      p->bin_start.as<int>(), p->bin_sizes.as<int>(), p->idx,    \
+                                      p->start.as<int4>(), p->wrec.as<float>(), c, fw);          \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    SPREAD_CASE(2) SPREAD_CASE(3) SPREAD_CASE(4) SPREAD_CASE(5) SPREAD_CASE(6) SPREAD_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef SPREAD_CASE
+  return cudaGetLastError();
+}
+
+constexpr int kInterpWarps = 4;
+
+template <int RANK>
+cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+#define INTERP_CASE(NS)                                                                          \
+  case NS: {                                                                                     \
+    auto k = interp_tile_f32_kernel<NS, RANK, kInterpWarps>;                                     \
+    if (p->tile_smem > 48 * 1024)                                                                \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);   \
+    k<<<grid, kInterpWarps * 32, p->tile_smem, st>>>(                                            \
+        p->M, g, p->msub, p->sub_total(), p->sub_start.as<int>(), p->bin_start.as<int>(),        \
+        p->bin_sizes.as<int>(), p->idx, p->start.as<int4>(), p->wrec.as<float>(), fw, c);        \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    INTERP_CASE(2) INTERP_CASE(3) INTERP_CASE(4) INTERP_CASE(5) INTERP_CASE(6) INTERP_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef INTERP_CASE
+  return cudaGetLastError();
+}
+
+template <typename F>
+int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
+  if (p->M == 0) return B200NUFFT_OK;
+  if (p->spread_method == 2) {
+    cudaError_t e = p->rank == 2
+        ? launch_spread_tile<2>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st)
+        : launch_spread_tile<3>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread tile launch: %s", cudaGetErrorString(e));
+  } else {
+    const int rows = p->rank == 1 ? 1 : (p->rank == 2 ? p->kp.ns : p->kp.ns * p->kp.ns);
+    spread_global_kernel<F><<<grid_for(p->M * rows, 256, 16), 256, 0, st>>>(
+        p->M, ntr, grid_geom(p), p->kp.ns, p->R, p->PX, p->PY, p->idx, p->start.as<int4>(),
+        p->wrec.as<F>(), static_cast<const Cplx<F>*>(c), static_cast<Cplx<F>*>(fw));
+    LAUNCH_OK(p);
+  }
+  p->launches++;
+  return B200NUFFT_OK;
+}
+
+template <typename F>
+int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
+  if (p->M == 0) return B200NUFFT_OK;
+  if (p->interp_method == 2) {
+    cudaError_t e = p->rank == 2
+        ? launch_interp_tile<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
+        : launch_interp_tile<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp tile launch: %s", cudaGetErrorString(e));
+  } else {
+    interp_global_kernel<F><<<grid_for(p->M, 128, 32), 128, 0, st>>>(
+        p->M, ntr, grid_geom(p), p->kp.ns, p->R, p->PX, p->PY, p->idx, p->start.as<int4>(),
+        p->wrec.as<F>(), static_cast<const Cplx<F>*>(fw), static_cast<Cplx<F>*>(c));
+    LAUNCH_OK(p);
+  }
+  p->launches++;
+  return B200NUFFT_OK;
+}
+
+int do_fft(b200nufft_plan* p, int ntr, cudaStream_t st) {
+  cufftHandle h = p->fft;
+  if (ntr != p->batch) {
+    if (!p->has_fft_rem || p->fft_rem_batch != ntr) {
+      if (p->has_fft_rem) cufftDestroy(p->fft_rem);
+      int n[3];
+      for (int d = 0; d < p->rank; ++d) n[d] = p->nf[p->rank - 1 - d];
+      cufftResult r = cufftPlanMany(&p->fft_rem, p->rank, n, nullptr, 1, 0, nullptr, 1, 0,
+                                    p->is_double ? CUFFT_Z2Z : CUFFT_C2C, ntr);
+      if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftPlanMany (remainder) failed: %d", (int)r);
+      p->has_fft_rem = true;
+      p->fft_rem_batch = ntr;
+    }
+    h = p->fft_rem;
+  }
+  cufftResult r = cufftSetStream(h, st);
+  if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftSetStream failed: %d", (int)r);
+  const int dir = p->fft_sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
+  if (p->is_double)
+    r = cufftExecZ2Z(h, p->fine.as<cufftDoubleComplex>(), p->fine.as<cufftDoubleComplex>(), dir);
+  else
+    r = cufftExecC2C(h, p->fine.as<cufftComplex>(), p->fine.as<cufftComplex>(), dir);
+  if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftExec failed: %d", (int)r);
+  p->launches++;
+  return B200NUFFT_OK;
+}
+
+template <typename F>
+int execute_impl(b200nufft_plan* p, void* c_, void* f_, cudaStream_t st) {
+  using C = Cplx<F>;
+  C* c = static_cast<C*>(c_);
+  C* f = static_cast<C*>(f_);
+  const ModeGeom mg = mode_geom(p);
+  const F* p1 = p->fser[0].as<F>();
+  const F* p2 = p->fser[1].as<F>();
+  const F* p3 = p->fser[2].as<F>();
+  const bool prof = p->opts.profile != 0;
+  float acc[3] = {0, 0, 0};
+  (void)acc;
+  for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
+    const int ntr = std::min(p->batch, p->ntransf - b0);
+    C* cb = c + static_cast<int64_t>(b0) * p->M;
+    C* fb = f + static_cast<int64_t>(b0) * p->n_modes_tot;
+    C* fw = p->fine.as<C>();
+    // With profiling on, only the LAST batch's stage events are kept (a stage = one launch).
+    if (p->type == 1) {
+      if (prof) cudaEventRecord(p->ev[0], st);
+      CUDA_OK(p, cudaMemsetAsync(fw, 0, sizeof(C) * p->nftot * ntr, st));
+      int rc = do_spread<F>(p, ntr, cb, fw, st);
+      if (rc) return rc;
+      if (prof) cudaEventRecord(p->ev[1], st);
+      rc = do_fft(p, ntr, st);
+      if (rc) return rc;
+      if (prof) cudaEventRecord(p->ev[2], st);
+      dim3 grid(ceil_div(p->n_modes_tot, 256), ntr);
+      deconvolve_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fw, fb);
+      LAUNCH_OK(p);
+      p->launches++;
+      if (prof) cudaEventRecord(p->ev[3], st);
+    } else {
+      if (prof) cudaEventRecord(p->ev[0], st);
+      dim3 grid(ceil_div(p->nftot, 256), ntr);
+      amplify_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fb, fw);
+      LAUNCH_OK(p);
+      p->launches++;
+      if (prof) cudaEventRecord(p->ev[1], st);
+      int rc = do_fft(p, ntr, st);
+      if (rc) return rc;
+      if (prof) cudaEventRecord(p->ev[2], st);
+      rc = do_interp<F>(p, ntr, fw, cb, st);
+      if (rc) return rc;
+      if (prof) cudaEventRecord(p->ev[3], st);
+    }
+  }
+  p->ev_exec = prof;
+  return B200NUFFT_OK;
+}
+
+template <typename F>
+int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, const void* y, const void* z,
+                    cudaStream_t st) {
+  if (M < 0 || M > 2000000000LL) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "invalid num_points %lld", (long long)M);
+  const bool prof = p->opts.profile != 0;
+  if (prof) cudaEventRecord(p->ev[4], st);
+  p->M = M;
+  p->points_set = true;
+  p->sub_bound = 0;
+  if (M == 0) {
+    if (prof) cudaEventRecord(p->ev[5], st);
+    p->ev_setpts = prof;
+    return B200NUFFT_OK;
+  }
+  const int rank = p->rank;
+  for (int d = 0; d < rank; ++d) CUDA_OK(p, p->folded[d].reserve(sizeof(F) * M));
+  CUDA_OK(p, p->keys0.reserve(sizeof(uint32_t) * M));
+  CUDA_OK(p, p->keys1.reserve(sizeof(uint32_t) * M));
+  CUDA_OK(p, p->vals0.reserve(sizeof(int) * M));
+  CUDA_OK(p, p->vals1.reserve(sizeof(int) * M));
+  CUDA_OK(p, p->hist.reserve(sizeof(int) * radix_hist_ints(M)));
+  CUDA_OK(p, p->start.reserve(sizeof(int4) * M));
+  CUDA_OK(p, p->wrec.reserve(sizeof(F) * M * p->R));
+
+  BinGeom bg;
+  bg.rank = rank;
+  bg.rounding = 0;
+  for (int d = 0; d < 3; ++d) { bg.nf[d] = p->nf[d]; bg.bin[d] = p->bin[d]; bg.nbins[d] = p->nbins[d]; }
+
+  CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * p->nbtot, st));
+  CUDA_OK(p, cudaMemsetAsync(p->range_flag(), 0, sizeof(int), st));
+  F lo, hi;
+  points_bounds<F>(p, &lo, &hi);
+  const int check = p->opts.check_points_range && p->opts.points_range != B200NUFFT_RANGE_INFINITE;
+  fold_key_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
+      M, layout, static_cast<const F*>(x), static_cast<const F*>(y), static_cast<const F*>(z),
+      p->opts.points_range, check, lo, hi, bg, p->folded[0].as<F>(), p->folded[1].as<F>(),
+      p->folded[2].as<F>(), p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
+      p->range_flag());
+  LAUNCH_OK(p);
+  p->launches++;
+
+  uint32_t* ks;
+  int* vs;
+  p->launches += radix_sort_pairs(p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->keys1.as<uint32_t>(),
+                                  p->vals1.as<int>(), M, ilog2_ceil(p->nbtot), p->hist.as<int>(),
+                                  p->scan_tmp(), &ks, &vs, st);
+  LAUNCH_OK(p);
+  p->idx = vs;
+
+  p->launches += exclusive_scan_i32(p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->nbtot,
+                                    p->scan_tmp(), nullptr, st);
+  subproblem_count_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub,
+                                                                  p->num_sub.as<int>());
+  p->launches++;
+  p->launches += exclusive_scan_i32(p->num_sub.as<int>(), p->sub_start.as<int>(), p->nbtot, p->scan_tmp(),
+                                    p->sub_total(), st);
+  LAUNCH_OK(p);
+  // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
+  // launch the bound, surplus CTAs exit on the device-side count.
+  p->sub_bound = std::min<int64_t>(p->nbtot, M) + M / p->msub;
+
+  const int align_x = (!p->is_double) ? 1 : 0;
+  stencil_record_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
+      M, rank, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns,
+      static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
+      p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
+  LAUNCH_OK(p);
+  p->launches++;
+
+  if (prof) cudaEventRecord(p->ev[5], st);
+  p->ev_setpts = prof;
+
+  if (check) {
+    CUDA_OK(p, cudaMemcpyAsync(p->h_flag, p->range_flag(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(p, cudaStreamSynchronize(st));
+    if (*p->h_flag) {
+      int d = 0;
+      while (d < 3 && !((*p->h_flag >> d) & 1)) ++d;
+      p->points_set = false;
+      return set_err(p, B200NUFFT_INVALID_ARGUMENT,
+                     "Found points outside expected range for dimension %d. Valid range is [%g, %g]. "
+                     "Check your points and/or set a less restrictive value for options.points_range.",
+                     d, (double)lo, (double)hi);
+    }
+  }
+  return B200NUFFT_OK;
+}
+
+template <typename F>
+int create_impl(b200nufft_plan* p) {
+  // ---- kernel + grid parameters (setup_spreader, set_grid_size) ----
+  const double sigma = 2.0;  // Plan<GPUDevice> always uses 2.0 (nufft_plan.cu.cc:1855-1857)
+  p->kp = make_kernel_params<F>(static_cast<F>(p->tol), sigma);
+  p->nftot = 1;
+  for (int d = 0; d < p->rank; ++d) {
+    if (!fine_grid_size(p->n_modes[d], sigma, p->kp.ns, p->opts.spread_only != 0, &p->nf[d])) {
+      return set_err(p, B200NUFFT_INVALID_ARGUMENT,
+                     "Invalid grid size: %lld. Value should be even, larger than the kernel (%d) and have no "
+                     "prime factors larger than 5.", (long long)p->n_modes[d], 2 * p->kp.ns);
+    }
+    p->nftot *= p->nf[d];
+  }
+  p->batch = p->opts.max_batch_size > 0 ? std::min(p->opts.max_batch_size, p->ntransf) : std::min(p->ntransf, 8);
+  if (p->nftot * p->batch > 2000000000LL) {
+    // shrink the batch rather than fail (the reference errors out above kMaxArraySize elements)
+    p->batch = static_cast<int>(std::max<int64_t>(1, 2000000000LL / p->nftot));
+  }
+  if (p->opts.spread_only) p->kernel_scale = kernel_scale_factor<F>(p->rank, p->kp);
+
+  // ---- weight record layout ----
+  const int ns = p->kp.ns;
+  p->PX = ns <= 7 ? 8 : ((ns + 1 + 3) / 4) * 4;
+  p->PY = ns <= 7 ? 8 : ((ns + 3) / 4) * 4;
+  p->R = p->PX + (p->rank > 1 ? p->PY : 0) + (p->rank > 2 ? p->PY : 0);
+
+  // ---- method + bin geometry ----
+  const bool tile_ok = !p->is_double && ns <= 7 && p->rank >= 2;
+  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? 2 : 1) : p->opts.spread_method;
+  p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 2 : 1) : p->opts.interp_method;
+  if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
+  int def_bin[3] = {1, 1, 1};
+  if (p->rank == 1) { def_bin[0] = 1024; }
+  else if (p->rank == 2) { def_bin[0] = 32; def_bin[1] = 32; }
+  else { def_bin[0] = 16; def_bin[1] = 16; def_bin[2] = (p->type == 2) ? 8 : 2; }
+  p->nbtot = 1;
+  for (int d = 0; d < 3; ++d) {
+    p->bin[d] = d < p->rank ? (p->opts.bin_dims[d] > 0 ? p->opts.bin_dims[d] : def_bin[d]) : 1;
+    p->nbins[d] = d < p->rank ? (p->nf[d] + p->bin[d] - 1) / p->bin[d] : 1;
+    p->nbtot *= p->nbins[d];
+  }
+  p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;
+  const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method == 2 : false;
+  const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method == 2 : false;
+  if (uses_tile || uses_tile_i) {
+    if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
+      return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
+    p->tile_smem = static_cast<size_t>(p->bin[0] + 8) * (p->bin[1] + 8) * (p->rank > 2 ? p->bin[2] + 8 : 1) * sizeof(float2);
+    if (p->tile_smem > 227 * 1024)
+      return set_err(p, B200NUFFT_RESOURCE_EXHAUSTED, "tile of %zu bytes exceeds shared memory", p->tile_smem);
+  }
+
+  // ---- deconvolution factors (host, then H2D; as the reference does, nufft_plan.cu.cc:1988-2021) ----
+  p->num_threads_compat = p->opts.num_threads_compat > 0
+      ? p->opts.num_threads_compat
+      : std::max(1u, std::thread::hardware_concurrency());
+  if (!p->opts.spread_only) {
+    for (int d = 0; d < p->rank; ++d) {
+      const int nc = p->nf[d] / 2 + 1;
+      p->fser_host[d].resize(sizeof(F) * nc);
+      kernel_fseries<F>(p->nf[d], p->kp, p->opts.fseries_mode, p->num_threads_compat,
+                        reinterpret_cast<F*>(p->fser_host[d].data()));
+      CUDA_OK(p, p->fser[d].reserve(sizeof(F) * nc));
+      CUDA_OK(p, cudaMemcpy(p->fser[d].p, p->fser_host[d].data(), sizeof(F) * nc, cudaMemcpyHostToDevice));
+    }
+    CUDA_OK(p, p->fine.reserve(sizeof(Cplx<F>) * p->nftot * p->batch));
+    int n[3];
+    for (int d = 0; d < p->rank; ++d) n[d] = p->nf[p->rank - 1 - d];
+    cufftResult r = cufftPlanMany(&p->fft, p->rank, n, nullptr, 1, 0, nullptr, 1, 0,
+                                  p->is_double ? CUFFT_Z2Z : CUFFT_C2C, p->batch);
+    if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftPlanMany failed: %d", (int)r);
+    p->has_fft = true;
+  }
+  CUDA_OK(p, p->bin_sizes.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->bin_start.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->num_sub.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->sub_start.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->misc.reserve(sizeof(int) * (kScanMaxBlocks + 8)));
+  CUDA_OK(p, cudaMallocHost(&p->h_flag, sizeof(int)));
+  if (p->opts.profile)
+    for (auto& e : p->ev) CUDA_OK(p, cudaEventCreate(&e));
+  return B200NUFFT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+void b200nufft_default_opts(b200nufft_opts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->points_range = B200NUFFT_RANGE_EXTENDED;
+}
+
+int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
+                          int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device) {
+  if (!out) return B200NUFFT_INVALID_ARGUMENT;
+  *out = nullptr;
+  auto fail = [&](int code, const std::string& m) { g_create_error = m; return code; };
+  if (type != 1 && type != 2) return fail(B200NUFFT_UNIMPLEMENTED, "type-3 transforms are not implemented");
+  if (rank < 1 || rank > 3) return fail(B200NUFFT_UNIMPLEMENTED, "rank must be 1, 2 or 3, but got: " + std::to_string(rank));
+  if (num_transforms < 1) return fail(B200NUFFT_INVALID_ARGUMENT, "num_transforms must be >= 1");
+  if (dtype != B200NUFFT_COMPLEX64 && dtype != B200NUFFT_COMPLEX128) return fail(B200NUFFT_INVALID_ARGUMENT, "invalid dtype");
+  if (fft_sign != 1 && fft_sign != -1) return fail(B200NUFFT_INVALID_ARGUMENT, "fft_sign must be -1 or +1");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(B200NUFFT_INTERNAL, std::string("no CUDA device available: ") + cudaGetErrorString(ce) +
+                                        " (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(B200NUFFT_INVALID_ARGUMENT, "invalid device ordinal");
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(B200NUFFT_INTERNAL, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+
+  b200nufft_plan* p = new b200nufft_plan();
+  p->type = type; p->rank = rank; p->fft_sign = fft_sign; p->ntransf = num_transforms;
+  p->dtype = dtype; p->is_double = dtype == B200NUFFT_COMPLEX128; p->device = device; p->tol = tol;
+  if (opts) p->opts = *opts; else b200nufft_default_opts(&p->opts);
+  p->n_modes_tot = 1;
+  for (int d = 0; d < rank; ++d) {
+    if (grid_dims[d] < 1 || grid_dims[d] > 2000000000LL) {
+      delete p;
+      return fail(B200NUFFT_INVALID_ARGUMENT, "invalid grid dimension");
+    }
+    p->n_modes[d] = grid_dims[d];
+    p->n_modes_tot *= grid_dims[d];
+  }
+  int rc = p->is_double ? create_impl<double>(p) : create_impl<float>(p);
+  if (rc != B200NUFFT_OK) {
+    g_create_error = p->err;
+    b200nufft_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return B200NUFFT_OK;
+}
+
+void b200nufft_plan_destroy(b200nufft_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->has_fft) cufftDestroy(p->fft);
+  if (p->has_fft_rem) cufftDestroy(p->fft_rem);
+  p->fine.release();
+  for (int d = 0; d < 3; ++d) { p->fser[d].release(); p->folded[d].release(); }
+  p->keys0.release(); p->keys1.release(); p->vals0.release(); p->vals1.release(); p->hist.release();
+  p->start.release(); p->wrec.release(); p->bin_sizes.release(); p->bin_start.release();
+  p->num_sub.release(); p->sub_start.release(); p->misc.release();
+  if (p->h_flag) cudaFreeHost(p->h_flag);
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  delete p;
+}
+
+int b200nufft_set_points(b200nufft_plan* p, int64_t M, const void* x, const void* y, const void* z, void* stream) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return p->is_double ? set_points_impl<double>(p, M, 0, x, y, z, st) : set_points_impl<float>(p, M, 0, x, y, z, st);
+}
+
+int b200nufft_set_points_interleaved(b200nufft_plan* p, int64_t M, const void* pts, void* stream) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return p->is_double ? set_points_impl<double>(p, M, 1, pts, nullptr, nullptr, st)
+                      : set_points_impl<float>(p, M, 1, pts, nullptr, nullptr, st);
+}
+
+int b200nufft_execute(b200nufft_plan* p, void* c, void* f, void* stream) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  if (p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "execute called on a spread-only plan");
+  if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before execute");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return p->is_double ? execute_impl<double>(p, c, f, st) : execute_impl<float>(p, c, f, st);
+}
+
+int b200nufft_interp(b200nufft_plan* p, void* c, const void* f, void* stream) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  if (!p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "interp needs a spread-only plan");
+  if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before interp");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t cs = p->is_double ? sizeof(double2) : sizeof(float2);
+  for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
+    const int ntr = std::min(p->batch, p->ntransf - b0);
+    char* cb = static_cast<char*>(c) + cs * b0 * p->M;
+    const char* fb = static_cast<const char*>(f) + cs * b0 * p->nftot;
+    int rc = p->is_double ? do_interp<double>(p, ntr, fb, cb, st) : do_interp<float>(p, ntr, fb, cb, st);
+    if (rc) return rc;
+    const int64_t n = static_cast<int64_t>(ntr) * p->M;
+    if (n > 0) {
+      if (p->is_double) scale_kernel<double><<<grid_for(n, 256), 256, 0, st>>>(n, p->kernel_scale, reinterpret_cast<double2*>(cb));
+      else scale_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(n, static_cast<float>(p->kernel_scale), reinterpret_cast<float2*>(cb));
+      p->launches++;
+    }
+  }
+  LAUNCH_OK(p);
+  return B200NUFFT_OK;
+}
+
+int b200nufft_spread(b200nufft_plan* p, const void* c, void* f, void* stream) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  if (!p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "spread needs a spread-only plan");
+  if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before spread");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t cs = p->is_double ? sizeof(double2) : sizeof(float2);
+  for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
+    const int ntr = std::min(p->batch, p->ntransf - b0);
+    const char* cb = static_cast<const char*>(c) + cs * b0 * p->M;
+    char* fb = static_cast<char*>(f) + cs * b0 * p->nftot;
+    CUDA_OK(p, cudaMemsetAsync(fb, 0, cs * p->nftot * ntr, st));
+    int rc = p->is_double ? do_spread<double>(p, ntr, cb, fb, st) : do_spread<float>(p, ntr, cb, fb, st);
+    if (rc) return rc;
+    const int64_t n = static_cast<int64_t>(ntr) * p->nftot;
+    if (p->is_double) scale_kernel<double><<<grid_for(n, 256), 256, 0, st>>>(n, p->kernel_scale, reinterpret_cast<double2*>(fb));
+    else scale_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(n, static_cast<float>(p->kernel_scale), reinterpret_cast<float2*>(fb));
+    p->launches++;
+  }
+  LAUNCH_OK(p);
+  return B200NUFFT_OK;
+}
+
+int b200nufft_get_sort(const b200nufft_plan* p, const int32_t** idx, const int32_t** bin_start,
+                       const int32_t** bin_sizes, int32_t* bin_count) {
+  if (!p || !p->points_set) return B200NUFFT_INVALID_ARGUMENT;
+  if (idx) *idx = p->idx;
+  if (bin_start) *bin_start = p->bin_start.as<int32_t>();
+  if (bin_sizes) *bin_sizes = p->bin_sizes.as<int32_t>();
+  if (bin_count) *bin_count = p->nbtot;
+  return B200NUFFT_OK;
+}
+
+int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const void* y, const void* z,
+                      const int* fine_dims, const int* bin_dims, int rounding, int32_t* idx_out,
+                      int32_t* bin_start_out, int32_t* bin_sizes_out, void* stream) {
+  if (rank < 1 || rank > 3 || M < 0) return B200NUFFT_INVALID_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BinGeom bg;
+  bg.rank = rank;
+  bg.rounding = rounding;
+  int nbtot = 1;
+  for (int d = 0; d < 3; ++d) {
+    bg.nf[d] = d < rank ? fine_dims[d] : 1;
+    bg.bin[d] = d < rank ? bin_dims[d] : 1;
+    bg.nbins[d] = d < rank ? (rounding == 0 ? (bg.nf[d] + bg.bin[d] - 1) / bg.bin[d] : bg.nf[d] / bg.bin[d] + 1) : 1;
+    nbtot *= bg.nbins[d];
+  }
+  if (cudaMemsetAsync(bin_sizes_out, 0, sizeof(int) * nbtot, st) != cudaSuccess) return B200NUFFT_INTERNAL;
+  DevBuf k0, k1, v0, v1, hist, tmp;
+  int rc = B200NUFFT_OK;
+  if (M > 0) {
+    if (k0.reserve(4 * M) || k1.reserve(4 * M) || v0.reserve(4 * M) || v1.reserve(4 * M) ||
+        hist.reserve(sizeof(int) * radix_hist_ints(M)) || tmp.reserve(sizeof(int) * (kScanMaxBlocks + 8))) {
+      rc = B200NUFFT_RESOURCE_EXHAUSTED;
+    } else {
+      if (is_double)
+        key_only_kernel<double><<<grid_for(M, 256), 256, 0, st>>>(M, (const double*)x, (const double*)y, (const double*)z, bg,
+                                                                 k0.as<uint32_t>(), v0.as<int>(), bin_sizes_out);
+      else
+        key_only_kernel<float><<<grid_for(M, 256), 256, 0, st>>>(M, (const float*)x, (const float*)y, (const float*)z, bg,
+                                                                k0.as<uint32_t>(), v0.as<int>(), bin_sizes_out);
+      uint32_t* ks; int* vs;
+      radix_sort_pairs(k0.as<uint32_t>(), v0.as<int>(), k1.as<uint32_t>(), v1.as<int>(), M, ilog2_ceil(nbtot),
+                       hist.as<int>(), tmp.as<int>(), &ks, &vs, st);
+      cudaMemcpyAsync(idx_out, vs, sizeof(int) * M, cudaMemcpyDeviceToDevice, st);
+    }
+  } else {
+    tmp.reserve(sizeof(int) * (kScanMaxBlocks + 8));
+  }
+  if (rc == B200NUFFT_OK) {
+    exclusive_scan_i32(bin_sizes_out, bin_start_out, nbtot, tmp.as<int>(), nullptr, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200NUFFT_INTERNAL;
+  }
+  k0.release(); k1.release(); v0.release(); v1.release(); hist.release(); tmp.release();
+  return rc;
+}
+
+int b200nufft_fold_rescale(int is_double, int points_range, int64_t M, const void* in, void* out, int fine_dim,
+                           void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0) return B200NUFFT_OK;
+  if (is_double)
+    fold_only_kernel<double><<<grid_for(M, 256), 256, 0, st>>>(M, (const double*)in, (double*)out, points_range, fine_dim);
+  else
+    fold_only_kernel<float><<<grid_for(M, 256), 256, 0, st>>>(M, (const float*)in, (float*)out, points_range, fine_dim);
+  return cudaGetLastError() == cudaSuccess ? B200NUFFT_OK : B200NUFFT_INTERNAL;
+}
+
+int b200nufft_get_info(const b200nufft_plan* p, b200nufft_info* info) {
+  if (!p || !info) return B200NUFFT_INVALID_ARGUMENT;
+  std::memset(info, 0, sizeof(*info));
+  info->kernel_width = p->kp.ns;
+  info->kernel_beta = p->kp.beta;
+  info->kernel_c = p->kp.c;
+  info->upsampling_factor = p->kp.sigma;
+  info->kernel_scale = p->kernel_scale;
+  for (int d = 0; d < 3; ++d) { info->fine_dims[d] = p->nf[d]; info->bin_dims[d] = p->bin[d]; info->num_bins[d] = p->nbins[d]; }
+  info->batch_size = p->batch;
+  info->num_threads_compat = p->num_threads_compat;
+  info->num_points = p->M;
+  info->subproblem_bound = p->sub_bound;
+  return B200NUFFT_OK;
+}
+
+int b200nufft_get_fseries(const b200nufft_plan* p, int dim, void* host_out) {
+  if (!p || dim < 0 || dim >= p->rank || p->fser_host[dim].empty()) return B200NUFFT_INVALID_ARGUMENT;
+  std::memcpy(host_out, p->fser_host[dim].data(), p->fser_host[dim].size());
+  return B200NUFFT_OK;
+}
+
+int b200nufft_get_timings(b200nufft_plan* p, float out[4]) {
+  if (!p || !p->opts.profile) return B200NUFFT_INVALID_ARGUMENT;
+  for (int i = 0; i < 4; ++i) out[i] = 0.f;
+  if (p->ev_exec) {
+    if (cudaEventSynchronize(p->ev[3]) != cudaSuccess) return B200NUFFT_INTERNAL;
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&b, p->ev[1], p->ev[2]);
+    cudaEventElapsedTime(&c, p->ev[2], p->ev[3]);
+    if (p->type == 1) { out[0] = a; out[1] = b; out[2] = c; }
+    else { out[2] = a; out[1] = b; out[0] = c; }
+  }
+  if (p->ev_setpts) {
+    if (cudaEventSynchronize(p->ev[5]) != cudaSuccess) return B200NUFFT_INTERNAL;
+    cudaEventElapsedTime(&out[3], p->ev[4], p->ev[5]);
+  }
+  return B200NUFFT_OK;
+}
+
+int64_t b200nufft_launch_count(const b200nufft_plan* p) { return p ? p->launches : 0; }
+const char* b200nufft_last_error(const b200nufft_plan* p) { return p ? p->err : "null plan"; }
+const char* b200nufft_last_create_error(void) { return g_create_error.c_str(); }
+
+int b200nufft_host_kernel_width(int is_double, double tol, double sigma) {
+  return is_double ? kernel_width_from_tol<double>(tol, sigma) : kernel_width_from_tol<float>(static_cast<float>(tol), sigma);
+}
+int b200nufft_host_next_smooth_int(int n) { return next_smooth_int(n); }
+int b200nufft_host_fseries(int is_double, int fine_dim, int kernel_width, int mode, int num_threads, void* out) {
+  if (kernel_width < 2 || kernel_width > kMaxKernelWidth || fine_dim < 2) return B200NUFFT_INVALID_ARGUMENT;
+  if (is_double)
+    kernel_fseries<double>(fine_dim, kernel_params_from_width<double>(kernel_width, 2.0), mode, num_threads,
+                           static_cast<double*>(out));
+  else
+    kernel_fseries<float>(fine_dim, kernel_params_from_width<float>(kernel_width, 2.0), mode, num_threads,
+                          static_cast<float*>(out));
+  return B200NUFFT_OK;
+}
+double b200nufft_host_scale_factor(int is_double, int rank, int kernel_width) {
+  if (is_double) return kernel_scale_factor<double>(rank, kernel_params_from_width<double>(kernel_width, 2.0));
+  return kernel_scale_factor<float>(rank, kernel_params_from_width<float>(kernel_width, 2.0));
+}
+int b200nufft_host_gauss_legendre(int n, double* nodes, double* weights) {
+  if (n < 1) return B200NUFFT_INVALID_ARGUMENT;
+  gauss_legendre(n, nodes, weights);
+  return B200NUFFT_OK;
+}
+const char* b200nufft_version(void) { return "b200nufft 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// points.cuh -- "points prep" kernels: range check, fold+rescale, bin keys, bin histogram, and
+// the per-point stencil records (start indices + ES kernel values) in bin-sorted order.
+// Behavioural references: FoldAndRescale functors nufft_plan.h:676-734; IsWithinRange :659-671;
+// bin rule CalcBinSizeNoGhost{1,2,3}DKernel nufft_plan.cu.cc:160-231 (GPU) and
+// binsort_singlethread nufft_plan.cc:475-531 (CPU); stencil start/offset and direct ES
+// evaluation nufft_plan.cc:1187-1201,1254-1289 / nufft_plan.cu.cc:838-846.
+#pragma once
+#include "dev_common.cuh"
+
+namespace b200 {
+
+enum { kRangeStrict = 0, kRangeExtended = 1, kRangeInfinite = 2 };
+
+template <typename F> struct MathConst;
+template <> struct MathConst<float> {
+  static constexpr float pi = 3.14159265358979329f;
+  static constexpr float two_pi = 6.283185307179586f;
+  static constexpr float inv_two_pi = 0.159154943091895336f;
+};
+template <> struct MathConst<double> {
+  static constexpr double pi = 3.14159265358979329;
+  static constexpr double two_pi = 6.283185307179586;
+  static constexpr double inv_two_pi = 0.159154943091895336;
+};
+
+// x -> fold(x) * (1/2pi) * nf, the same FloatType operations in the same order as the reference.
+template <typename F>
+__device__ __forceinline__ F fold_rescale(F x, int range, int nf) {
+  const F pi = MathConst<F>::pi;
+  F s;
+  if (range == kRangeStrict) {
+    s = add_rn(x, pi);
+  } else if (range == kRangeExtended) {
+    if (x > pi) s = sub_rn(x, pi);
+    else if (x < -pi) s = add_rn(x, mul_rn(F(3.0), pi));
+    else s = add_rn(x, pi);
+  } else {
+    s = fmod(add_rn(x, pi), MathConst<F>::two_pi);
+    if (s < F(0.0)) s = add_rn(s, MathConst<F>::two_pi);
+  }
+  return mul_rn(mul_rn(s, MathConst<F>::inv_two_pi), static_cast<F>(nf));
+}
+
+struct BinGeom {
+  int rank;
+  int nf[3];
+  int bin[3];
+  int nbins[3];
+  int rounding;  // 0: GPU rule floor+clamp; 1: CPU rule int() truncation (nbins = nf/bin+1)
+};
+
+template <typename F>
+__device__ __forceinline__ int bin_of(F x, int bin_dim, int nbins, int rounding) {
+  // float divide by an int bin size, as the reference writes it (x / bin_size_x)
+  F q = x / static_cast<F>(bin_dim);
+  int b;
+  if (rounding == 0) {
+    b = static_cast<int>(floor(q));
+    b = b >= nbins ? b - 1 : b;
+    b = b < 0 ? 0 : b;
+    b = b >= nbins ? nbins - 1 : b;  // memory safety for out-of-range inputs; no-op for x in [0, nf]
+  } else {
+    b = static_cast<int>(q);
+    b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);  // safety only
+  }
+  return b;
+}
+
+// Reads raw points (layout 0: `rank` separate arrays; layout 1: interleaved [M][rank] with the
+// coordinate order reversed, i.e. the op's own layout), optionally range-checks, folds and
+// writes folded coords (SoA), the bin key, and the identity value for the sort.
+template <typename F>
+__global__ void __launch_bounds__(256)
+fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __restrict__ p1,
+                const F* __restrict__ p2, int range, int check, F lo, F hi, BinGeom g,
+                F* __restrict__ f0, F* __restrict__ f1, F* __restrict__ f2,
+                uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes,
+                int* __restrict__ range_flag) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
+    F x[3] = {F(0), F(0), F(0)};
+    if (layout == 0) {
+      x[0] = p0[i];
+      if (g.rank > 1) x[1] = p1[i];
+      if (g.rank > 2) x[2] = p2[i];
+    } else {
+      for (int d = 0; d < g.rank; ++d) x[d] = p0[i * g.rank + (g.rank - 1 - d)];
+    }
+    int bad = 0;
+    int key = 0;
+    int mul = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < g.rank) {
+        if (check && !((x[d] > lo) && (x[d] < hi))) bad |= (1 << d);
+        F xf = fold_rescale<F>(x[d], range, g.nf[d]);
+        x[d] = xf;
+        key += mul * bin_of<F>(xf, g.bin[d], g.nbins[d], g.rounding);
+        mul *= g.nbins[d];
+      }
+    }
+    f0[i] = x[0];
+    if (g.rank > 1) f1[i] = x[1];
+    if (g.rank > 2) f2[i] = x[2];
+    keys[i] = static_cast<uint32_t>(key);
+    vals[i] = static_cast<int>(i);
+    // Warp-aggregated histogram: one atomic per distinct bin per warp (hot bins, e.g. the
+    // k-space centre of a radial trajectory, would otherwise serialise).
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader) atomicAdd(&bin_sizes[key], __popc(peers));
+    if (bad) atomicOr(range_flag, bad);
+  }
+}
+
+// Keys only, from already folded coordinates (parity hook b200nufft_binsort).
+template <typename F>
+__global__ void __launch_bounds__(256)
+key_only_kernel(int64_t M, const F* __restrict__ f0, const F* __restrict__ f1, const F* __restrict__ f2,
+                BinGeom g, uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
+    int key = bin_of<F>(f0[i], g.bin[0], g.nbins[0], g.rounding);
+    if (g.rank > 1) key += g.nbins[0] * bin_of<F>(f1[i], g.bin[1], g.nbins[1], g.rounding);
+    if (g.rank > 2) key += g.nbins[0] * g.nbins[1] * bin_of<F>(f2[i], g.bin[2], g.nbins[2], g.rounding);
+    keys[i] = static_cast<uint32_t>(key);
+    vals[i] = static_cast<int>(i);
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader) atomicAdd(&bin_sizes[key], __popc(peers));
+  }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+fold_only_kernel(int64_t M, const F* __restrict__ in, F* __restrict__ out, int range, int nf) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride)
+    out[i] = fold_rescale<F>(in[i], range, nf);
+}
+
+// num_sub[b] = ceil(bin_sizes[b] / msub)   (CalcSubproblemKernel, nufft_plan.cu.cc:304-310)
+__global__ void __launch_bounds__(256)
+subproblem_count_kernel(const int* __restrict__ bin_sizes, int nb, int msub, int* __restrict__ num_sub) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) num_sub[i] = (bin_sizes[i] + msub - 1) / msub;
+}
+
+// ES kernel value phi(x) = exp(beta * sqrt(1 - c x^2)) for |x| < ns/2, else 0, with the
+// reference CPU evaluator's roundings (evaluate_kernel_vector, nufft_plan.cc:1254-1289):
+// c*x*x in FloatType; 1 - ., sqrt and the product with beta in double; rounded to FloatType;
+// then exp (evaluated in double here and rounded once = correctly rounded FloatType exp).
+template <typename F>
+__device__ __forceinline__ F es_eval(F x, F beta, F c, F half_width) {
+  F t = mul_rn(mul_rn(c, x), x);
+  double a = 1.0 - static_cast<double>(t);
+  a = a < 0.0 ? 0.0 : a;
+  F e = static_cast<F>(static_cast<double>(beta) * sqrt(a));
+  F k = static_cast<F>(exp(static_cast<double>(e)));
+  return (fabs(x) >= half_width) ? F(0) : k;
+}
+
+// Per-point stencil record, in sorted order j (point id idx[j]):
+//   start[j] = {x0, i1y, i1z, shift}   x0 = i1x - shift, shift = (i1x & 1) if align_x else 0
+//   wrec[j][R] = { wx[PX], wy[PY] (rank>1), wz[PY] (rank>2) }
+//     wx[shift + k] = phi(x1 + k), k < ns, zero elsewhere (PX >= ns + 1)
+//     wy[k] = phi(y1 + k), wz[k] = phi(z1 + k), k < ns, zero padded
+// with i1 = ceil(x - ns/2), x1 = (F)i1 - x  (nufft_plan.cc:1187-1193).
+template <typename F>
+__global__ void __launch_bounds__(256)
+stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F* __restrict__ f0,
+                      const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
+                      int align_x, int R, int PX, int PY, int4* __restrict__ start, F* __restrict__ wrec) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < M; j += stride) {
+    const int i = idx[j];
+    int4 st = make_int4(0, 0, 0, 0);
+    F* w = wrec + j * R;
+    {
+      const F x = f0[i];
+      const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
+      const F x1 = sub_rn(static_cast<F>(i1), x);
+      const int shift = align_x ? (i1 & 1) : 0;
+      st.x = i1 - shift;
+      st.w = shift;
+      for (int k = 0; k < PX; ++k) {
+        const int t = k - shift;
+        w[k] = (t >= 0 && t < ns) ? es_eval<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
+      }
+      w += PX;
+    }
+    if (rank > 1) {
+      const F y = f1[i];
+      const int i1 = static_cast<int>(ceil(sub_rn(y, half_width)));
+      const F y1 = sub_rn(static_cast<F>(i1), y);
+      st.y = i1;
+      for (int k = 0; k < PY; ++k)
+        w[k] = (k < ns) ? es_eval<F>(add_rn(y1, static_cast<F>(k)), beta, c, half_width) : F(0);
+      w += PY;
+    }
+    if (rank > 2) {
+      const F z = f2[i];
+      const int i1 = static_cast<int>(ceil(sub_rn(z, half_width)));
+      const F z1 = sub_rn(static_cast<F>(i1), z);
+      st.z = i1;
+      for (int k = 0; k < PY; ++k)
+        w[k] = (k < ns) ? es_eval<F>(add_rn(z1, static_cast<F>(k)), beta, c, half_width) : F(0);
+    }
+    start[j] = st;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,238 @@
+// scan_sort.cuh -- hand-written device primitives for the bin-sort: an exclusive scan of int32
+// arrays and a stable LSD radix sort of (key, value) pairs. Deterministic and stable: the bin-sort
+// permutation must be bit-reproducible (the reference's is atomic-arrival ordered,
+// nufft_plan.cu.cc:171,196,228; the stable order is the one it produces when atomics resolve
+// in index order).
+#pragma once
+#include "dev_common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan, three phases: per-block chunk sums -> scan of <=1024 block sums -> per-block
+// sequential tile scan with carry. out may alias in. total (optional) receives the grand total.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 1024
+constexpr int kScanMaxBlocks = 1024;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread (256 threads); returns exclusive prefix, and
+// the block total through *total_out (same for all threads).
+__device__ __forceinline__ int block_excl_scan_256(int v, int* total_out) {
+  __shared__ int warp_sums[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = warp_incl_scan(v);
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int wprefix = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    int s = warp_sums[w];
+    if (w < warp) wprefix += s;
+    total += s;
+  }
+  __syncthreads();
+  *total_out = total;
+  return wprefix + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_chunk_sums_kernel(const int* __restrict__ in, int64_t n, int64_t chunk, int* __restrict__ block_sums) {
+  const int64_t beg = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int64_t end = min(beg + chunk, n);
+  int s = 0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += kScanThreads) s += in[i];
+  int total;
+  block_excl_scan_256(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanMaxBlocks)
+scan_block_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total_out) {
+  __shared__ int wsum[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int v = t < nb ? block_sums[t] : 0;
+  int incl = warp_incl_scan(v);
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int s = wsum[lane];
+    int si = warp_incl_scan(s);
+    wsum[lane] = si - s;
+  }
+  __syncthreads();
+  int excl = wsum[warp] + incl - v;
+  if (t < nb) block_sums[t] = excl;
+  if (t == nb - 1 && total_out) *total_out = excl + v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int64_t n, int64_t chunk,
+                  const int* __restrict__ block_offs) {
+  const int64_t beg = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int64_t end = min(beg + chunk, n);
+  int carry = block_offs[blockIdx.x];
+  for (int64_t base = beg; base < end; base += kScanTile) {
+    int v[kScanItems];
+    int tsum = 0;
+    const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      v[k] = (i0 + k < end) ? in[i0 + k] : 0;
+      tsum += v[k];
+    }
+    int total;
+    int excl = block_excl_scan_256(tsum, &total) + carry;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (i0 + k < end) out[i0 + k] = excl;
+      excl += v[k];
+    }
+    carry += total;
+  }
+}
+
+// tmp must hold kScanMaxBlocks ints. Returns the number of kernels launched.
+inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_out,
+                              cudaStream_t stream) {
+  if (n <= 0) {
+    if (total_out) cudaMemsetAsync(total_out, 0, sizeof(int), stream);
+    return 0;
+  }
+  int nb = static_cast<int>(std::min<int64_t>(kScanMaxBlocks, (n + 4 * kScanTile - 1) / (4 * kScanTile)));
+  int64_t chunk = (n + nb - 1) / nb;
+  chunk = ((chunk + kScanTile - 1) / kScanTile) * kScanTile;
+  nb = static_cast<int>((n + chunk - 1) / chunk);
+  scan_chunk_sums_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, chunk, tmp);
+  scan_block_sums_kernel<<<1, kScanMaxBlocks, 0, stream>>>(tmp, nb, total_out);
+  scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, out, n, chunk, tmp);
+  return 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stable LSD radix sort, 8-bit digits, (uint32 key, int32 value) pairs. Tile = 8 warps x 256
+// consecutive elements per warp; a warp walks its 256 elements in 8 rounds of 32 lanes, so the
+// (warp, round, lane) order IS the element order and ranks are stable by construction.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortWarps = 8;
+constexpr int kSortThreads = kSortWarps * 32;
+constexpr int kSortRounds = 8;
+constexpr int kSortPerWarp = 32 * kSortRounds;             // 256
+constexpr int kSortTile = kSortWarps * kSortPerWarp;       // 2048
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblk,
+                  int* __restrict__ hist /*[kRadix][nblk]*/) {
+  __shared__ int cnt[kRadix];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortTile / kSortThreads; ++r) {
+    int64_t i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & (kRadix - 1)], 1);
+  }
+  __syncthreads();
+  hist[static_cast<int64_t>(threadIdx.x) * nblk + blockIdx.x] = cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
+                     uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int64_t n,
+                     int shift, int nblk, const int* __restrict__ offs /*[kRadix][nblk] scanned*/) {
+  __shared__ int cnt[kSortWarps][kRadix];   // running per-warp digit counts
+  __shared__ int gbase[kRadix];             // global base of each digit for this block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  gbase[threadIdx.x] = offs[static_cast<int64_t>(threadIdx.x) * nblk + blockIdx.x];
+  __syncthreads();
+
+  const int64_t wbase = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * kSortPerWarp;
+  uint32_t key[kSortRounds];
+  int val[kSortRounds];
+  int rank[kSortRounds];
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    key[r] = ok ? keys_in[i] : 0xffffffffu;
+    val[r] = ok ? vals_in[i] : 0;
+    // Invalid lanes use digit kRadix (out of range) so they never match a real digit.
+    const unsigned dig = ok ? ((key[r] >> shift) & (kRadix - 1)) : kRadix;
+    const unsigned peers = __match_any_sync(0xffffffffu, dig);
+    const int before = __popc(peers & ((1u << lane) - 1u));
+    int prev = 0;
+    if (ok) prev = cnt[warp][dig];
+    __syncwarp();
+    if (ok && before == 0) cnt[warp][dig] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + before;
+  }
+  __syncthreads();
+  // Exclusive prefix over warps for each digit (thread d handles digit d).
+  {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      int c = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const unsigned dig = (key[r] >> shift) & (kRadix - 1);
+      const int64_t pos = static_cast<int64_t>(gbase[dig]) + cnt[warp][dig] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
+    }
+  }
+}
+
+// Sorts n pairs by the low `key_bits` bits of the key. Buffers: (k0,v0) hold the input; (k1,v1)
+// are scratch of the same size; hist holds kRadix*nblk ints; scan_tmp kScanMaxBlocks ints.
+// On return *keys_sorted/*vals_sorted point at whichever buffer holds the result.
+inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_t n, int key_bits,
+                            int* hist, int* scan_tmp, uint32_t** keys_sorted, int** vals_sorted,
+                            cudaStream_t stream) {
+  int launches = 0;
+  uint32_t* kin = k0; int* vin = v0; uint32_t* kout = k1; int* vout = v1;
+  if (n > 0) {
+    const int nblk = static_cast<int>((n + kSortTile - 1) / kSortTile);
+    const int passes = key_bits <= 0 ? 0 : (key_bits + kRadixBits - 1) / kRadixBits;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = p * kRadixBits;
+      radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
+      launches += 1 + exclusive_scan_i32(hist, hist, static_cast<int64_t>(kRadix) * nblk, scan_tmp, nullptr, stream);
+      radix_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
+      launches += 1;
+      std::swap(kin, kout);
+      std::swap(vin, vout);
+    }
+  }
+  *keys_sorted = kin;
+  *vals_sorted = vin;
+  return launches;
+}
+
+inline int64_t radix_hist_ints(int64_t n) {
+  return static_cast<int64_t>(kRadix) * ((n + kSortTile - 1) / kSortTile) + 1;
+}
+
+}  // namespace b200
