@@ -10,6 +10,8 @@
 //                            subproblem, lanes laid over the stencil (row = lane / QX, cell pair =
 //                            lane % QX): 128-bit conflict-free shared loads, butterfly reduction.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "dev_common.cuh"
 #include "spread.cuh"
 
@@ -51,28 +53,29 @@ interp_global_kernel(int64_t M, int ntr, GridGeom g, int ns, int R, int PX, int 
   }
 }
 
+// One CTA (WARPS warps) per (subproblem, transform). The (bin + halo) tile is copied into shared
+// memory with 16-byte cp.async (LDGSTS) copies, then each warp takes batches of 32 points: lane l
+// prefetches the record of its point of the NEXT batch (weights, start, point id) while the warp
+// gathers the current batch from the tile; records are staged per warp in shared memory
+// ({tile offset, wx[8], wy[8], wz[8]}), results are reduced by butterfly shuffles and scattered to
+// c[idx] once per batch.
 template <int NS, int RANK, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-interp_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ sub_total,
-                       const int* __restrict__ sub_start, const int* __restrict__ bin_start,
-                       const int* __restrict__ bin_sizes, const int* __restrict__ idx,
-                       const int4* __restrict__ start, const float* __restrict__ wrec,
+interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
+                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                       const int4* __restrict__ start, const float4* __restrict__ wrec4,
                        const float2* __restrict__ fw, float2* __restrict__ c) {
   constexpr int QX = (NS + 2) / 2;
-  constexpr int RPI = NS;
-  constexpr int R = 8 * RANK;
-  extern __shared__ float4 tile4[];
-  float2* tile = reinterpret_cast<float2*>(tile4);
+  constexpr int C4 = 2 * RANK;
+  constexpr int SW = StageRec<RANK>::kWords;
+  extern __shared__ float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
-  const int nbtot = g.nbins[0] * g.nbins[1] * g.nbins[2];
-  const int b = find_bin_of_subproblem(sub_start, nbtot, s);
-  const int within = s - sub_start[b];
-  const int p0 = bin_start[b] + within * msub;
-  const int np = min(msub, bin_sizes[b] - within * msub);
+  const int4 sd = sub_desc[s];
+  const int b = sd.x, p0 = sd.y, np = sd.z;
 
   const int TX = g.bin[0] + 8, TY = g.bin[1] + 8;
   const int TZ = RANK > 2 ? g.bin[2] + 8 : 1;
@@ -82,73 +85,99 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ 
   const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
   const int ncell = TX * TY * TZ;
   const int TXH = TX / 2;
+  float4* tile4 = smem4;
+  const float2* tile = reinterpret_cast<const float2*>(tile4);
+  float* stage = reinterpret_cast<float*>(smem4 + ncell / 2) + warp * 32 * SW;   // per warp [32][SW]
 
   const float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
   float2* ct = c + static_cast<int64_t>(t) * M;
 
-  // Stage the tile (two cells per 128-bit load; nf and the tile origin are even so a pair never
-  // straddles the periodic boundary).
-  for (int i = threadIdx.x; i < ncell / 2; i += WARPS * 32) {
+  // ---- prefetch the first batch's records while the tile streams in ----
+  float4 w4[C4];
+  int4 st_n = make_int4(0, 0, 0, 0);
+  int id_n = 0;
+  auto fetch = [&](int first) {
+    const int pl = first + lane;
+    if (pl < np) {
+      const int64_t j = p0 + pl;
+#pragma unroll
+      for (int k = 0; k < C4; ++k) w4[k] = wrec4[j * C4 + k];
+      st_n = start[j];
+      id_n = idx[j];
+    }
+  };
+  fetch(warp * 32);
+
+  // Stage the tile (two cells per 16-byte async copy; nf and the tile origin are even so a pair
+  // never straddles the periodic boundary).
+  for (int i = tid; i < ncell / 2; i += WARPS * 32) {
     const int ix = i % TXH;
     const int iy = (i / TXH) % TY;
     const int iz = i / (TXH * TY);
     const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
     const int gy = mod_idx(oy + iy, g.nf[1]);
     const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
-    tile4[i] = *reinterpret_cast<const float4*>(fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx);
+    const float2* src = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
+    __pipeline_memcpy_async(&tile4[i], src, 16);
   }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
   __syncthreads();
 
   const int q = lane % QX;
   const int r = lane / QX;
-  const bool row_ok = r < RPI;
+  const bool row_ok = r < NS;
   const int lane_off = r * TX + 2 * q;
+  const int zstride4 = TY * TX / 2;
 
-  for (int base = warp * 32; base < np; base += WARPS * 32) {
-    const int jl = p0 + base + lane;
-    int off_l = -1;
-    int pid_l = 0;
-    if (base + lane < np) {
-      pid_l = idx[jl];
-      const int4 st = start[jl];
-      const int rx = st.x - ox, ry = st.y - oy, rz = RANK > 2 ? st.z - oz : 0;
-      const bool fits = rx >= 0 && rx + 2 * QX <= TX && ry >= 0 && ry + NS <= TY &&
-                        (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
-      off_l = fits ? (rz * TY + ry) * TX + rx : -1;
-    }
-    float2 res_l = make_float2(0.f, 0.f);
-    const int cnt = min(32, np - base);
-    for (int p = 0; p < cnt; ++p) {
-      const int64_t j = p0 + base + p;
-      const float wv = lane < R ? wrec[j * R + lane] : 0.f;
-      const int boff = __shfl_sync(0xffffffffu, off_l, p);
-      const float wxa = __shfl_sync(0xffffffffu, wv, 2 * q);
-      const float wxb = __shfl_sync(0xffffffffu, wv, 2 * q + 1);
-      const float wyr = __shfl_sync(0xffffffffu, wv, 8 + (row_ok ? r : 0));
-      float re = 0.f, im = 0.f;
-      if (RANK == 2) {
-        if (row_ok && boff >= 0) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + boff + lane_off);
-          re = wyr * (v.x * wxa + v.z * wxb);
-          im = wyr * (v.y * wxa + v.w * wxb);
-        }
-      } else {
-        float wz[NS];
+  for (int first = warp * 32; first < np; first += WARPS * 32) {
+    // ---- stage this lane's point, then prefetch the next batch ----
+    const int id_cur = id_n;
+    {
+      const int pl = first + lane;
+      float4* rec4 = reinterpret_cast<float4*>(stage + lane * SW);
+      int off = -1;
+      if (pl < np) {
+        const int rx = st_n.x - ox, ry = st_n.y - oy, rz = RANK > 2 ? st_n.z - oz : 0;
+        const bool fits = rx >= 0 && rx + 2 * QX <= TX && ry >= 0 && ry + NS <= TY &&
+                          (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
+        if (fits) off = (rz * TY + ry) * TX + rx;
+      }
+      rec4[0] = make_float4(__int_as_float(off), 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int dz = 0; dz < NS; ++dz) wz[dz] = __shfl_sync(0xffffffffu, wv, 16 + dz);
-        if (row_ok && boff >= 0) {
-          const float4* ptr = reinterpret_cast<const float4*>(tile + boff + lane_off);
-          const int zstride = TY * TX / 2;
+      for (int k = 0; k < C4; ++k) rec4[1 + k] = w4[k];
+    }
+    __syncwarp();
+    fetch(first + WARPS * 32);
+
+    float2 res_l = make_float2(0.f, 0.f);
+    const int cnt = min(32, np - first);
+    for (int p = 0; p < cnt; ++p) {
+      const float* rec = stage + p * SW;
+      const int off = __float_as_int(rec[0]);
+      float re = 0.f, im = 0.f;
+      if (row_ok && off >= 0) {
+        const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
+        const float wy = rec[12 + r];
+        const float4* ptr = reinterpret_cast<const float4*>(tile + off + lane_off);
+        if (RANK == 2) {
+          const float4 v = *ptr;
+          re = wy * (v.x * wx.x + v.z * wx.y);
+          im = wy * (v.y * wx.x + v.w * wx.y);
+        } else {
           float4 v[NS];
 #pragma unroll
-          for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride];
+          for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride4];
+          const float4 wza = *reinterpret_cast<const float4*>(rec + 20);
+          const float4 wzb = *reinterpret_cast<const float4*>(rec + 24);
+          const float wz[8] = {wza.x, wza.y, wza.z, wza.w, wzb.x, wzb.y, wzb.z, wzb.w};
 #pragma unroll
           for (int dz = 0; dz < NS; ++dz) {
-            re += wz[dz] * (v[dz].x * wxa + v[dz].z * wxb);
-            im += wz[dz] * (v[dz].y * wxa + v[dz].w * wxb);
+            re += wz[dz] * (v[dz].x * wx.x + v[dz].z * wx.y);
+            im += wz[dz] * (v[dz].y * wx.x + v[dz].w * wx.y);
           }
-          re *= wyr;
-          im *= wyr;
+          re *= wy;
+          im *= wy;
         }
       }
 #pragma unroll
@@ -158,8 +187,15 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ 
       }
       if (lane == p) res_l = make_float2(re, im);
     }
-    if (base + lane < np) ct[pid_l] = res_l;
+    if (first + lane < np) ct[id_cur] = res_l;
+    __syncwarp();
   }
+}
+
+template <int RANK, int WARPS>
+inline size_t interp_tile_smem_bytes(const int* bin) {
+  const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
+  return ncell * sizeof(float2) + static_cast<size_t>(WARPS) * 32 * StageRec<RANK>::kWords * sizeof(float);
 }
 
 }  // namespace b200

@@ -85,12 +85,14 @@ struct b200nufft_plan {
   int64_t M = 0;
   bool points_set = false;
   DevBuf folded[3], keys0, keys1, vals0, vals1, hist, start, wrec;
-  DevBuf bin_sizes, bin_start, num_sub, sub_start, misc;  // misc: scan tmp[1024] + sub_total + range flag
+  DevBuf bin_sizes, bin_start, num_sub, sub_start, sub_desc, misc;  // misc: scan tmp[1024] + sub_total + range flag
   int* idx = nullptr;      // points at vals0 or vals1
   int64_t sub_bound = 0;
   int* h_flag = nullptr;   // pinned
 
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_batch;  // 4 events per batch of the last execute (profile mode)
+  int ev_batches = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4],[5]: set_points
   bool ev_exec = false, ev_setpts = false;
   int64_t launches = 0;
   char err[768] = {0};
@@ -169,18 +171,21 @@ void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
 // ------------------------------------------------------------------------------------------
 // Tile-kernel dispatch on the kernel width.
 // ------------------------------------------------------------------------------------------
-template <int RANK>
+constexpr int kInterpWarps = 4;
+constexpr int kSpreadWarps3D = 4;   // warps sharing one 3D tile (z-plane ownership)
+
+template <int RANK, int WPT>
 cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = spread_tile_smem_bytes<RANK, WPT>(p->bin);
 #define SPREAD_CASE(NS)                                                                          \
   case NS: {                                                                                     \
-    auto k = spread_tile_f32_kernel<NS, RANK>;                                                   \
-    if (p->tile_smem > 48 * 1024)                                                                \
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);   \
-    k<<<grid, 32, p->tile_smem, st>>>(p->M, g, p->msub, p->sub_total(), p->sub_start.as<int>(),  \
-                                      p->bin_start.as<int>(), p->bin_sizes.as<int>(), p->idx,    \
-                                      p->start.as<int4>(), p->wrec.as<float>(), c, fw);          \
+    auto k = spread_tile_f32_kernel<NS, RANK, WPT>;                                              \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, WPT * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,     \
+                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw);           \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -191,20 +196,19 @@ cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c
   return cudaGetLastError();
 }
 
-constexpr int kInterpWarps = 4;
-
 template <int RANK>
 cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = interp_tile_smem_bytes<RANK, kInterpWarps>(p->bin);
 #define INTERP_CASE(NS)                                                                          \
   case NS: {                                                                                     \
     auto k = interp_tile_f32_kernel<NS, RANK, kInterpWarps>;                                     \
-    if (p->tile_smem > 48 * 1024)                                                                \
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tile_smem);   \
-    k<<<grid, kInterpWarps * 32, p->tile_smem, st>>>(                                            \
-        p->M, g, p->msub, p->sub_total(), p->sub_start.as<int>(), p->bin_start.as<int>(),        \
-        p->bin_sizes.as<int>(), p->idx, p->start.as<int4>(), p->wrec.as<float>(), fw, c);        \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, kInterpWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),    \
+                                             p->idx, p->start.as<int4>(), p->wrec.as<float4>(),  \
+                                             fw, c);                                             \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -220,8 +224,8 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
   if (p->M == 0) return B200NUFFT_OK;
   if (p->spread_method == 2) {
     cudaError_t e = p->rank == 2
-        ? launch_spread_tile<2>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st)
-        : launch_spread_tile<3>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st);
+        ? launch_spread_tile<2, 1>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st)
+        : launch_spread_tile<3, kSpreadWarps3D>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread tile launch: %s", cudaGetErrorString(e));
   } else {
     const int rows = p->rank == 1 ? 1 : (p->rank == 2 ? p->kp.ns : p->kp.ns * p->kp.ns);
@@ -289,44 +293,52 @@ int execute_impl(b200nufft_plan* p, void* c_, void* f_, cudaStream_t st) {
   const F* p2 = p->fser[1].as<F>();
   const F* p3 = p->fser[2].as<F>();
   const bool prof = p->opts.profile != 0;
-  float acc[3] = {0, 0, 0};
-  (void)acc;
-  for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
+  int bi = 0;
+  for (int b0 = 0; b0 < p->ntransf; b0 += p->batch, ++bi) {
     const int ntr = std::min(p->batch, p->ntransf - b0);
+    cudaEvent_t* ev = nullptr;
+    if (prof) {
+      while (static_cast<int>(p->ev_batch.size()) < 4 * (bi + 1)) {
+        cudaEvent_t e;
+        CUDA_OK(p, cudaEventCreate(&e));
+        p->ev_batch.push_back(e);
+      }
+      ev = p->ev_batch.data() + 4 * bi;
+    }
     C* cb = c + static_cast<int64_t>(b0) * p->M;
     C* fb = f + static_cast<int64_t>(b0) * p->n_modes_tot;
     C* fw = p->fine.as<C>();
-    // With profiling on, only the LAST batch's stage events are kept (a stage = one launch).
     if (p->type == 1) {
-      if (prof) cudaEventRecord(p->ev[0], st);
+      if (prof) cudaEventRecord(ev[0], st);
       CUDA_OK(p, cudaMemsetAsync(fw, 0, sizeof(C) * p->nftot * ntr, st));
       int rc = do_spread<F>(p, ntr, cb, fw, st);
       if (rc) return rc;
-      if (prof) cudaEventRecord(p->ev[1], st);
+      if (prof) cudaEventRecord(ev[1], st);
       rc = do_fft(p, ntr, st);
       if (rc) return rc;
-      if (prof) cudaEventRecord(p->ev[2], st);
+      if (prof) cudaEventRecord(ev[2], st);
       dim3 grid(ceil_div(p->n_modes_tot, 256), ntr);
       deconvolve_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fw, fb);
       LAUNCH_OK(p);
       p->launches++;
-      if (prof) cudaEventRecord(p->ev[3], st);
+      if (prof) cudaEventRecord(ev[3], st);
     } else {
-      if (prof) cudaEventRecord(p->ev[0], st);
+      if (prof) cudaEventRecord(ev[0], st);
       dim3 grid(ceil_div(p->nftot, 256), ntr);
       amplify_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fb, fw);
       LAUNCH_OK(p);
       p->launches++;
-      if (prof) cudaEventRecord(p->ev[1], st);
+      if (prof) cudaEventRecord(ev[1], st);
       int rc = do_fft(p, ntr, st);
       if (rc) return rc;
-      if (prof) cudaEventRecord(p->ev[2], st);
+      if (prof) cudaEventRecord(ev[2], st);
       rc = do_interp<F>(p, ntr, fw, cb, st);
       if (rc) return rc;
-      if (prof) cudaEventRecord(p->ev[3], st);
+      if (prof) cudaEventRecord(ev[3], st);
     }
   }
   p->ev_exec = prof;
+  p->ev_batches = bi;
   return B200NUFFT_OK;
 }
 
@@ -391,6 +403,12 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
   // launch the bound, surplus CTAs exit on the device-side count.
   p->sub_bound = std::min<int64_t>(p->nbtot, M) + M / p->msub;
+  CUDA_OK(p, p->sub_desc.reserve(sizeof(int4) * (p->sub_bound + 1)));
+  subproblem_desc_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(
+      p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
+      p->sub_desc.as<int4>());
+  LAUNCH_OK(p);
+  p->launches++;
 
   const int align_x = (!p->is_double) ? 1 : 0;
   stencil_record_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
@@ -467,7 +485,10 @@ int create_impl(b200nufft_plan* p) {
   if (uses_tile || uses_tile_i) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
-    p->tile_smem = static_cast<size_t>(p->bin[0] + 8) * (p->bin[1] + 8) * (p->rank > 2 ? p->bin[2] + 8 : 1) * sizeof(float2);
+    size_t need = 0;
+    if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
+    if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
+    p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)
       return set_err(p, B200NUFFT_RESOURCE_EXHAUSTED, "tile of %zu bytes exceeds shared memory", p->tile_smem);
   }
@@ -499,8 +520,10 @@ int create_impl(b200nufft_plan* p) {
   CUDA_OK(p, p->sub_start.reserve(sizeof(int) * (p->nbtot + 1)));
   CUDA_OK(p, p->misc.reserve(sizeof(int) * (kScanMaxBlocks + 8)));
   CUDA_OK(p, cudaMallocHost(&p->h_flag, sizeof(int)));
-  if (p->opts.profile)
-    for (auto& e : p->ev) CUDA_OK(p, cudaEventCreate(&e));
+  if (p->opts.profile) {
+    CUDA_OK(p, cudaEventCreate(&p->ev[4]));
+    CUDA_OK(p, cudaEventCreate(&p->ev[5]));
+  }
   return B200NUFFT_OK;
 }
 
@@ -567,9 +590,10 @@ void b200nufft_plan_destroy(b200nufft_plan* p) {
   for (int d = 0; d < 3; ++d) { p->fser[d].release(); p->folded[d].release(); }
   p->keys0.release(); p->keys1.release(); p->vals0.release(); p->vals1.release(); p->hist.release();
   p->start.release(); p->wrec.release(); p->bin_sizes.release(); p->bin_start.release();
-  p->num_sub.release(); p->sub_start.release(); p->misc.release();
+  p->num_sub.release(); p->sub_start.release(); p->sub_desc.release(); p->misc.release();
   if (p->h_flag) cudaFreeHost(p->h_flag);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : p->ev_batch) cudaEventDestroy(e);
   delete p;
 }
 
@@ -731,13 +755,17 @@ int b200nufft_get_timings(b200nufft_plan* p, float out[4]) {
   if (!p || !p->opts.profile) return B200NUFFT_INVALID_ARGUMENT;
   for (int i = 0; i < 4; ++i) out[i] = 0.f;
   if (p->ev_exec) {
-    if (cudaEventSynchronize(p->ev[3]) != cudaSuccess) return B200NUFFT_INTERNAL;
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, p->ev[0], p->ev[1]);
-    cudaEventElapsedTime(&b, p->ev[1], p->ev[2]);
-    cudaEventElapsedTime(&c, p->ev[2], p->ev[3]);
-    if (p->type == 1) { out[0] = a; out[1] = b; out[2] = c; }
-    else { out[2] = a; out[1] = b; out[0] = c; }
+    // Sum over the batches of the last execute.
+    for (int bi = 0; bi < p->ev_batches; ++bi) {
+      cudaEvent_t* ev = p->ev_batch.data() + 4 * bi;
+      if (cudaEventSynchronize(ev[3]) != cudaSuccess) return B200NUFFT_INTERNAL;
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      cudaEventElapsedTime(&c, ev[2], ev[3]);
+      if (p->type == 1) { out[0] += a; out[1] += b; out[2] += c; }
+      else { out[2] += a; out[1] += b; out[0] += c; }
+    }
   }
   if (p->ev_setpts) {
     if (cudaEventSynchronize(p->ev[5]) != cudaSuccess) return B200NUFFT_INTERNAL;

@@ -148,6 +148,20 @@ subproblem_count_kernel(const int* __restrict__ bin_sizes, int nb, int msub, int
   if (i < nb) num_sub[i] = (bin_sizes[i] + msub - 1) / msub;
 }
 
+// sub_desc[s] = {bin, first sorted point, point count, 0} for every subproblem s, so that a CTA
+// finds its work with one 16-byte load (replaces MapBinToSubproblemKernel, nufft_plan.cu.cc:312-320).
+__global__ void __launch_bounds__(256)
+subproblem_desc_kernel(const int* __restrict__ bin_sizes, const int* __restrict__ bin_start,
+                       const int* __restrict__ sub_start, int nb, int msub, int4* __restrict__ sub_desc) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int size = bin_sizes[b];
+  const int n = (size + msub - 1) / msub;
+  const int s0 = sub_start[b], p0 = bin_start[b];
+  for (int k = 0; k < n; ++k)
+    sub_desc[s0 + k] = make_int4(b, p0 + k * msub, min(msub, size - k * msub), 0);
+}
+
 // ES kernel value phi(x) = exp(beta * sqrt(1 - c x^2)) for |x| < ns/2, else 0, with the
 // reference CPU evaluator's roundings (evaluate_kernel_vector, nufft_plan.cc:1254-1289):
 // c*x*x in FloatType; 1 - ., sqrt and the product with beta in double; rounded to FloatType;

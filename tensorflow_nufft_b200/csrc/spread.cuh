@@ -80,42 +80,45 @@ spread_global_kernel(int64_t M, int ntr, GridGeom g, int ns, int R, int PX, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory tile spreader (complex64, ns <= 7, rank 2 or 3). One warp per CTA.
-// Work item = (subproblem, transform). Tile = (bin + 8)^rank cells of float2.
+// Shared-memory tile spreader (complex64, ns <= 7, rank 2 or 3).
+// Work item = (subproblem, transform); CTA = WPT warps sharing ONE tile of (bin + 8)^rank float2
+// cells. WPT = 1 in 2D. In 3D the tile's z-planes are dealt round-robin to the WPT warps
+// (plane p belongs to warp p % WPT), every warp walks all points of the subproblem and updates
+// only the planes it owns: exclusive ownership, so still no atomics, with WPT times the warps
+// per tile for latency hiding.
+// Points are consumed in batches of 32*WPT through a double-buffered shared-memory stage: lane l
+// of warp w fetches the record of point (32 w + l) of the NEXT batch from HBM (weights, start
+// index, strength via idx) while the CTA processes the current one; at the batch boundary each
+// lane writes {tile offset, c*wx[8], wy[8], wz[8]} for its point, one barrier, and the loop
+// goes on. All shared accesses in the inner loop are conflict-free 128-bit (tile pitch = 8 mod
+// 16 cells, stage record stride = 4 mod 32 words).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_bin_of_subproblem(const int* __restrict__ sub_start, int nb, int s) {
-  // largest b with sub_start[b] <= s  (sub_start is an exclusive scan, non-decreasing)
-  int lo = 0, hi = nb - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (sub_start[mid] <= s) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
+template <int RANK> struct StageRec {
+  // words: [0] tile offset (cells) or -1, [1] tile z of the stencil start, [2] Re c, [3] Im c,
+  //        [4..11] wx, [12..19] wy, [20..27] wz (3D)
+  static constexpr int kWords = RANK == 3 ? 28 : 20;
+};
 
-template <int NS, int RANK>
-__global__ void __launch_bounds__(32)
-spread_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ sub_total,
-                       const int* __restrict__ sub_start, const int* __restrict__ bin_start,
-                       const int* __restrict__ bin_sizes, const int* __restrict__ idx,
-                       const int4* __restrict__ start, const float* __restrict__ wrec /*[M][8*RANK]*/,
+template <int NS, int RANK, int WPT>
+__global__ void __launch_bounds__(WPT * 32)
+spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
+                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                       const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][2*RANK]*/,
                        const float2* __restrict__ c, float2* __restrict__ fw) {
   constexpr int QX = (NS + 2) / 2;      // float4 lanes per stencil row: covers NS+1 cells
-  constexpr int RPI = NS;               // rows per instruction (lanes r = lane / QX < NS active)
-  static_assert(QX * RPI <= 32, "stencil slab must fit one warp");
-  constexpr int R = 8 * RANK;           // floats per weight record
-  extern __shared__ float4 tile4[];     // [TZ][TY][TX/2] pairs of cells
-  float2* tile = reinterpret_cast<float2*>(tile4);
+  static_assert(QX * NS <= 32, "stencil slab must fit one warp");
+  constexpr int C4 = 2 * RANK;          // float4 chunks per weight record
+  constexpr int SW = StageRec<RANK>::kWords;
+  constexpr int BS = 32;                // points per batch (staged by warp 0, one point per lane)
+  constexpr int NBUF = WPT > 1 ? 2 : 1;
+  extern __shared__ float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
-  const int nbtot = g.nbins[0] * g.nbins[1] * g.nbins[2];
-  const int b = find_bin_of_subproblem(sub_start, nbtot, s);
-  const int within = s - sub_start[b];
-  const int p0 = bin_start[b] + within * msub;
-  const int np = min(msub, bin_sizes[b] - within * msub);
+  const int4 sd = sub_desc[s];
+  const int b = sd.x, p0 = sd.y, np = sd.z;
 
   const int TX = g.bin[0] + 8, TY = g.bin[1] + 8;
   const int TZ = RANK > 2 ? g.bin[2] + 8 : 1;
@@ -124,79 +127,125 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ 
   const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
   const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
   const int ncell = TX * TY * TZ;
+  float4* tile4 = smem4;
+  float2* tile = reinterpret_cast<float2*>(tile4);
+  float* stage = reinterpret_cast<float*>(smem4 + ncell / 2);   // [NBUF][BS][SW]
 
-  for (int i = lane; i < ncell / 2; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
+  for (int i = tid; i < ncell / 2; i += WPT * 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int q = lane % QX;
   const int r = lane / QX;
-  const bool row_ok = r < RPI;
-  const int lane_off = r * TX + 2 * q;   // cells, within a z-plane, relative to the point's base
+  const bool row_ok = r < NS;
+  const int lane_off = r * TX + 2 * q;   // cells, within a z-plane, relative to the stencil start
+  const int zstride4 = TY * TX / 2;
 
   const float2* ct = c + static_cast<int64_t>(t) * M;
   float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
 
-  for (int base = 0; base < np; base += 32) {
-    // Each lane prefetches one point's header: strength (gather through idx) and tile offset.
-    const int jl = p0 + base + lane;
-    float2 c_l = make_float2(0.f, 0.f);
-    int off_l = 0;
-    if (base + lane < np) {
-      const int4 st = start[jl];
-      const int rx = st.x - ox, ry = st.y - oy, rz = RANK > 2 ? st.z - oz : 0;
+  // ---- software pipeline registers (warp 0): this lane's point of the next batch ----
+  float4 w4[C4];
+  int4 st_n = make_int4(0, 0, 0, 0);
+  float2 c_n = make_float2(0.f, 0.f);
+  int id_n2 = 0;
+  auto fetch = [&](int bb) {
+    // weights + start + strength (through the id fetched one call earlier) for batch bb, and the
+    // point id for batch bb + 1
+    const int pl = bb * BS + lane;
+    if (pl < np) {
+      const int64_t j = p0 + pl;
+#pragma unroll
+      for (int k = 0; k < C4; ++k) w4[k] = wrec4[j * C4 + k];
+      st_n = start[j];
+      c_n = ct[id_n2];
+    }
+    const int pl2 = (bb + 1) * BS + lane;
+    if (pl2 < np) id_n2 = idx[p0 + pl2];
+  };
+  auto stage_write = [&](int bb) {
+    const int pl = bb * BS + lane;
+    float4* rec4 = reinterpret_cast<float4*>(stage + ((bb % NBUF) * BS + lane) * SW);
+    int off = -1, tz = 0;
+    if (pl < np) {
+      const int rx = st_n.x - ox, ry = st_n.y - oy, rz = RANK > 2 ? st_n.z - oz : 0;
       // Memory safety for coordinates outside the declared points_range: such a stencil does not
       // lie in this bin's tile and the point is dropped (the reference's behaviour is undefined).
       const bool fits = rx >= 0 && rx + 2 * QX <= TX && ry >= 0 && ry + NS <= TY &&
                         (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
-      if (fits) {
-        c_l = ct[idx[jl]];
-        off_l = (rz * TY + ry) * TX + rx;
-      }
+      if (fits) { off = (rz * TY + ry) * TX + rx; tz = rz; }
     }
-    const int cnt = min(32, np - base);
+    rec4[0] = make_float4(__int_as_float(off), __int_as_float(tz), c_n.x, c_n.y);
+#pragma unroll
+    for (int k = 0; k < C4; ++k) rec4[1 + k] = w4[k];
+  };
+  if (warp == 0) {
+    if (lane < np) id_n2 = idx[p0 + lane];
+    fetch(0);
+  }
+
+  const int nbatch = (np + BS - 1) / BS;
+  for (int bb = 0; bb < nbatch; ++bb) {
+    if (warp == 0) stage_write(bb);
+    __syncthreads();   // stage visible (and, first time, the zeroed tile)
+    if (warp == 0 && bb + 1 < nbatch) fetch(bb + 1);
+
+    const float* sbuf = stage + (bb % NBUF) * BS * SW;
+    const int cnt = min(BS, np - bb * BS);
     for (int p = 0; p < cnt; ++p) {
-      const int64_t j = p0 + base + p;
-      const float wv = lane < R ? wrec[j * R + lane] : 0.f;
-      const float cre = __shfl_sync(0xffffffffu, c_l.x, p);
-      const float cim = __shfl_sync(0xffffffffu, c_l.y, p);
-      const int boff = __shfl_sync(0xffffffffu, off_l, p);
-      const float wxa = __shfl_sync(0xffffffffu, wv, 2 * q);
-      const float wxb = __shfl_sync(0xffffffffu, wv, 2 * q + 1);
-      const float wyr = __shfl_sync(0xffffffffu, wv, 8 + (row_ok ? r : 0));
-      const float4 cx = make_float4(cre * wxa, cim * wxa, cre * wxb, cim * wxb);
-      if (RANK == 2) {
-        if (row_ok) {
-          float4* ptr = reinterpret_cast<float4*>(tile + boff + lane_off);
-          float4 v = *ptr;
-          v.x += wyr * cx.x; v.y += wyr * cx.y; v.z += wyr * cx.z; v.w += wyr * cx.w;
-          *ptr = v;
-        }
-      } else {
-        float4 v[NS];
-        float wz[NS];
-#pragma unroll
-        for (int dz = 0; dz < NS; ++dz) wz[dz] = __shfl_sync(0xffffffffu, wv, 16 + dz);
-        if (row_ok) {
-          float4* ptr = reinterpret_cast<float4*>(tile + boff + lane_off);
-          const int zstride = TY * TX / 2;
-#pragma unroll
-          for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride];
-#pragma unroll
-          for (int dz = 0; dz < NS; ++dz) {
-            const float w = wyr * wz[dz];
-            v[dz].x += w * cx.x; v[dz].y += w * cx.y; v[dz].z += w * cx.z; v[dz].w += w * cx.w;
+      const float* rec = sbuf + p * SW;
+      const float4 hdr = *reinterpret_cast<const float4*>(rec);
+      const int off = __float_as_int(hdr.x);
+      if (off >= 0) {
+        if (RANK == 2) {
+          if (row_ok) {
+            const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
+            const float wy = rec[12 + r];
+            const float a = hdr.z * wy, bq = hdr.w * wy;
+            float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off);
+            float4 v = *ptr;
+            v.x += a * wx.x; v.y += bq * wx.x; v.z += a * wx.y; v.w += bq * wx.y;
+            *ptr = v;
           }
+        } else {
+          const int tz = __float_as_int(hdr.y);
+          // first stencil plane owned by this warp: (tz + dz) % WPT == warp
+          int dz0 = (warp - tz) % WPT;
+          dz0 = dz0 < 0 ? dz0 + WPT : dz0;
+          if (row_ok && dz0 < NS) {
+            const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
+            const float wy = rec[12 + r];
+            const float4 cx = make_float4(hdr.z * wx.x, hdr.w * wx.x, hdr.z * wx.y, hdr.w * wx.y);
+            float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off);
+            constexpr int KMAX = (NS + WPT - 1) / WPT;
+            float4 v[KMAX];
+            float w[KMAX];
 #pragma unroll
-          for (int dz = 0; dz < NS; ++dz) ptr[dz * zstride] = v[dz];
+            for (int k = 0; k < KMAX; ++k) {
+              const int dz = dz0 + k * WPT;
+              if (dz < NS) {
+                v[k] = ptr[dz * zstride4];
+                w[k] = wy * rec[20 + dz];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              const int dz = dz0 + k * WPT;
+              if (dz < NS) {
+                v[k].x += w[k] * cx.x; v[k].y += w[k] * cx.y; v[k].z += w[k] * cx.z; v[k].w += w[k] * cx.w;
+                ptr[dz * zstride4] = v[k];
+              }
+            }
+          }
         }
       }
       __syncwarp();
     }
+    if (NBUF == 1) __syncwarp();
   }
+  __syncthreads();
 
   // Flush: two complex cells per REDG.ADD.F32x4; periodic wrap; untouched (zero) pairs skipped.
   const int TXH = TX / 2;
-  for (int i = lane; i < ncell / 2; i += 32) {
+  for (int i = tid; i < ncell / 2; i += WPT * 32) {
     const float4 v = tile4[i];
     if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
     const int ix = i % TXH;
@@ -208,6 +257,12 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, int msub, const int* __restrict__ 
     float2* dst = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
     red_add(reinterpret_cast<float4*>(dst), v);
   }
+}
+
+template <int RANK, int WPT>
+inline size_t spread_tile_smem_bytes(const int* bin) {
+  const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
+  return ncell * sizeof(float2) + static_cast<size_t>(WPT > 1 ? 2 : 1) * 32 * StageRec<RANK>::kWords * sizeof(float);
 }
 
 }  // namespace b200

@@ -49,6 +49,14 @@ def _get_plan(key_args, opt_kwargs):
   return plan
 
 
+def _to_host(t):
+  """Device -> pinned host copy (torch's caching host allocator makes the pinned buffer cheap)."""
+  out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+  out.copy_(t, non_blocking=True)
+  torch.cuda.current_stream().synchronize()
+  return out
+
+
 def _complex_dtype(real_dtype):
   return {torch.float32: torch.complex64, torch.float64: torch.complex128}[real_dtype]
 
@@ -149,7 +157,7 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
 
   if any(d == 0 for d in target_shape):
     out = torch.zeros(target_shape, dtype=source.dtype, device=device)
-    return out.cpu() if host_io else out
+    return _to_host(out) if host_io else out
 
   src_b = src.reshape(source_batch + source_elem)
   pts_b = pts.reshape(points_batch + [num_points, rank])
@@ -222,7 +230,7 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
     inv[ax] = pos
   tgt = tgt.permute(inv + list(range(nb, nb + len(target_elem)))).contiguous()
   tgt = tgt.reshape(target_shape)
-  return tgt.cpu() if host_io else tgt
+  return _to_host(tgt) if host_io else tgt
 
 
 def _sum_to_shape(x, shape):
