@@ -142,6 +142,10 @@ int b200nufft_binsort(int is_double, int rank, int64_t num_points, const void* x
 int b200nufft_fold_rescale(int is_double, int points_range, int64_t num_points, const void* in,
                            void* out, int fine_dim, void* stream);
 
+/* Test helper for the parity hooks: synchronous device -> host copy of plan-owned arrays
+ * (cudaMemcpy). Not used on the hot path. */
+int b200nufft_copy_to_host(void* dst_host, const void* src_device, size_t bytes);
+
 int b200nufft_get_info(const b200nufft_plan* plan, b200nufft_info* info);
 
 /* Copies the deconvolution factors of dimension `dim` (fine_dims[dim]/2+1 reals, FloatType) to

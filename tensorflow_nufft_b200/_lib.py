@@ -82,6 +82,7 @@ SIGNATURES = [
       ctypes.POINTER(ctypes.c_int), ctypes.c_int, _P, _P, _P, _P]),
     ("b200nufft_fold_rescale", ctypes.c_int,
      [ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, ctypes.c_int, _P]),
+    ("b200nufft_copy_to_host", ctypes.c_int, [_P, _P, ctypes.c_size_t]),
     ("b200nufft_get_info", ctypes.c_int, [_P, ctypes.POINTER(Info)]),
     ("b200nufft_get_fseries", ctypes.c_int, [_P, ctypes.c_int, _P]),
     ("b200nufft_get_timings", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
@@ -190,6 +191,19 @@ class Plan:
     self._check(lib().b200nufft_get_sort(self._h, ctypes.byref(idx), ctypes.byref(bs),
                                          ctypes.byref(bz), ctypes.byref(n)))
     return idx.value, bs.value, bz.value, n.value
+
+  def sort_arrays(self):
+    """Host copies (numpy int32) of idx[M], bin_start[bins], bin_sizes[bins]."""
+    import numpy as np
+    idx, bs, bz, n = self.sort_pointers()
+    m = int(self.info().num_points)
+    out = []
+    for ptr, cnt in ((idx, m), (bs, n), (bz, n)):
+      a = np.empty(cnt, np.int32)
+      if cnt:
+        self._check(lib().b200nufft_copy_to_host(a.ctypes.data, ptr, 4 * cnt))
+      out.append(a)
+    return out
 
   def fseries(self, dim, real_np_dtype):
     import numpy as np

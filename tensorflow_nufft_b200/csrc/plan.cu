@@ -729,6 +729,11 @@ int b200nufft_fold_rescale(int is_double, int points_range, int64_t M, const voi
   return cudaGetLastError() == cudaSuccess ? B200NUFFT_OK : B200NUFFT_INTERNAL;
 }
 
+int b200nufft_copy_to_host(void* dst_host, const void* src_device, size_t bytes) {
+  return cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? B200NUFFT_OK
+                                                                                         : B200NUFFT_INTERNAL;
+}
+
 int b200nufft_get_info(const b200nufft_plan* p, b200nufft_info* info) {
   if (!p || !info) return B200NUFFT_INVALID_ARGUMENT;
   std::memset(info, 0, sizeof(*info));
