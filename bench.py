@@ -232,7 +232,7 @@ def run_ours(args, cfg, rank_id, world, device):
                  "l2": "inputs larger than L2 (no flush needed)" if h2d > 126e6 else "working set below L2 size",
                  "step": "set_points + execute, all coils"},
       "stages_ms": {k: round(v, 4) for k, v in stage.items()},
-      "roofline": {"bound": "hbm", "kernel": "spread_tile_f32_kernel" if ttype == 1 else "interp_tile_f32_kernel",
+      "roofline": {"bound": "hbm", "kernel": ("spread_ws_f32_kernel" if rank == 2 else "spread_tile_f32_kernel") if ttype == 1 else "interp_tile_f32_kernel",
                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,

@@ -41,18 +41,22 @@ if __name__ == "__main__":
   which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
   if "cfg1" in which:
     run("cfg1-radial-256", 2, (256, 256), H.radial_points(200, 500), 1, (1, 2))
-    run("cfg1-radial-256-t1", 1, (256, 256), H.radial_points(200, 500), 1, (1, 2))
+    run("cfg1-radial-256-t1", 1, (256, 256), H.radial_points(200, 500), 1, (1, 2, 3))
   if "cfg2" in which:
     p = H.spiral_points(32, 62500)
-    run("cfg2-spiral-512-T8", 1, (512, 512), p, 8, (1, 2))
+    run("cfg2-spiral-512-T8", 1, (512, 512), p, 8, (2, 3))
     run("cfg2-spiral-512-T8-type2", 2, (512, 512), p, 8, (1, 2))
   if "cfg3" in which:
     p = H.uniform_points(8000000, 3, 3)
-    run("cfg3-uniform-128", 1, (128, 128, 128), p, 1, (1, 2))
+    run("cfg3-uniform-128", 1, (128, 128, 128), p, 1, (2,), bin_dims=(16, 16, 2))
+    run("cfg3-uniform-128-ws-16x16x4", 1, (128, 128, 128), p, 1, (3,), bin_dims=(16, 16, 4))
+    run("cfg3-uniform-128-ws-16x16x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(16, 16, 8))
+    run("cfg3-uniform-128-ws-16x8x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(16, 8, 8))
+    run("cfg3-uniform-128-ws-32x8x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(32, 8, 8))
     run("cfg3-uniform-128-type2", 2, (128, 128, 128), p, 1, (1, 2))
     run("cfg3-uniform-128-type2-bin2", 2, (128, 128, 128), p, 1, (2,), bin_dims=(16, 16, 2))
-    run("cfg3-uniform-128-bin4", 1, (128, 128, 128), p, 1, (2,), bin_dims=(16, 16, 4))
   if "cfg4" in which:
     p = H.stack_of_stars_points(125, 125, 256)
     run("cfg4-sos-256-T2", 2, (256, 256, 256), p, 2, (1, 2))
-    run("cfg4-sos-256-T2-type1", 1, (256, 256, 256), p, 2, (1, 2))
+    run("cfg4-sos-256-T2-type1", 1, (256, 256, 256), p, 2, (2,), bin_dims=(16, 16, 2))
+    run("cfg4-sos-256-T2-type1-ws", 1, (256, 256, 256), p, 2, (3,))

@@ -143,49 +143,89 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                           (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
         if (fits) off = (rz * TY + ry) * TX + rx;
       }
-      rec4[0] = make_float4(__int_as_float(off), 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < C4; ++k) rec4[1 + k] = w4[k];
+      for (int k = 0; k < C4; ++k) rec4[k] = w4[k];
+      rec4[6] = make_float4(__int_as_float(off), 0.f, 0.f, 0.f);
     }
     __syncwarp();
     fetch(first + WARPS * 32);
 
     float2 res_l = make_float2(0.f, 0.f);
     const int cnt = min(32, np - first);
-    for (int p = 0; p < cnt; ++p) {
-      const float* rec = stage + p * SW;
-      const int off = __float_as_int(rec[0]);
-      float re = 0.f, im = 0.f;
-      if (row_ok && off >= 0) {
-        const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
-        const float wy = rec[12 + r];
-        const float4* ptr = reinterpret_cast<const float4*>(tile + off + lane_off);
-        if (RANK == 2) {
-          const float4 v = *ptr;
-          re = wy * (v.x * wx.x + v.z * wx.y);
-          im = wy * (v.y * wx.x + v.w * wx.y);
-        } else {
-          float4 v[NS];
+    // Points are processed four at a time so that the butterfly reduction can be shared: the four
+    // (re, im) partial sums are folded with a transposing reduction (9 + 9 shuffles per 4 points
+    // instead of 40), and the four gathers are independent (ILP across points).
+    for (int p4 = 0; p4 < cnt; p4 += 4) {
+      float re[4], im[4];
 #pragma unroll
-          for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride4];
-          const float4 wza = *reinterpret_cast<const float4*>(rec + 20);
-          const float4 wzb = *reinterpret_cast<const float4*>(rec + 24);
-          const float wz[8] = {wza.x, wza.y, wza.z, wza.w, wzb.x, wzb.y, wzb.z, wzb.w};
+      for (int u = 0; u < 4; ++u) {
+        re[u] = 0.f;
+        im[u] = 0.f;
+        const int p = p4 + u;
+        if (p < cnt) {
+          const float* rec = stage + p * SW;
+          const int off = __float_as_int(rec[24]);
+          if (row_ok && off >= 0) {
+            const float2 wx = *reinterpret_cast<const float2*>(rec + 2 * q);
+            const float wy = rec[8 + r];
+            const float4* ptr = reinterpret_cast<const float4*>(tile + off + lane_off);
+            if (RANK == 2) {
+              const float4 v = *ptr;
+              re[u] = wy * (v.x * wx.x + v.z * wx.y);
+              im[u] = wy * (v.y * wx.x + v.w * wx.y);
+            } else {
+              float4 v[NS];
 #pragma unroll
-          for (int dz = 0; dz < NS; ++dz) {
-            re += wz[dz] * (v[dz].x * wx.x + v[dz].z * wx.y);
-            im += wz[dz] * (v[dz].y * wx.x + v[dz].w * wx.y);
+              for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride4];
+              float wz[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 t2 = *reinterpret_cast<const float2*>(rec + 16 + 2 * k);
+                wz[2 * k] = t2.x;
+                wz[2 * k + 1] = t2.y;
+              }
+              float ar = 0.f, ai = 0.f;
+#pragma unroll
+              for (int dz = 0; dz < NS; ++dz) {
+                ar += wz[dz] * (v[dz].x * wx.x + v[dz].z * wx.y);
+                ai += wz[dz] * (v[dz].y * wx.x + v[dz].w * wx.y);
+              }
+              re[u] = ar * wy;
+              im[u] = ai * wy;
+            }
           }
-          re *= wy;
-          im *= wy;
         }
       }
+      // Transposing butterfly: after the xor-16 and xor-8 steps each lane holds ONE of the four
+      // sums (selected by lane bits 4 and 3); three more steps finish it.
+      {
+        const bool hi16 = lane & 16, hi8 = lane & 8;
+        float a0 = hi16 ? re[0] : re[1], k0 = hi16 ? re[1] : re[0];
+        float a1 = hi16 ? re[2] : re[3], k1 = hi16 ? re[3] : re[2];
+        k0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        float a2 = hi8 ? k0 : k1, kr = hi8 ? k1 : k0;
+        kr += __shfl_xor_sync(0xffffffffu, a2, 8);
+        float b0 = hi16 ? im[0] : im[1], m0 = hi16 ? im[1] : im[0];
+        float b1 = hi16 ? im[2] : im[3], m1 = hi16 ? im[3] : im[2];
+        m0 += __shfl_xor_sync(0xffffffffu, b0, 16);
+        m1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+        float b2 = hi8 ? m0 : m1, ki = hi8 ? m1 : m0;
+        ki += __shfl_xor_sync(0xffffffffu, b2, 8);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
+        for (int o = 4; o > 0; o >>= 1) {
+          kr += __shfl_xor_sync(0xffffffffu, kr, o);
+          ki += __shfl_xor_sync(0xffffffffu, ki, o);
+        }
+        // lane bits (4,3) = (hi16, hi8) select the point: kept value index = 2*hi8 + hi16
+        const int which = (hi8 ? 2 : 0) + (hi16 ? 1 : 0);
+        // lanes 0, 16, 8, 24 hold points p4+0, p4+1, p4+2, p4+3; hand each to lane (p4 + which)
+        const int src_lane = ((lane - p4) & 1 ? 16 : 0) | ((lane - p4) & 2 ? 8 : 0);
+        const float rr = __shfl_sync(0xffffffffu, kr, src_lane);
+        const float ri = __shfl_sync(0xffffffffu, ki, src_lane);
+        (void)which;
+        if (lane >= p4 && lane < p4 + 4) res_l = make_float2(rr, ri);
       }
-      if (lane == p) res_l = make_float2(re, im);
     }
     if (first + lane < np) ct[id_cur] = res_l;
     __syncwarp();

@@ -23,6 +23,7 @@
 #include "points.cuh"
 #include "scan_sort.cuh"
 #include "spread.cuh"
+#include "spread_ws.cuh"
 
 using namespace b200;
 
@@ -72,6 +73,7 @@ struct b200nufft_plan {
   int PX = 8, PY = 8, R = 8;
   int num_threads_compat = 1;
   int spread_method = 1, interp_method = 1;
+  bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   size_t tile_smem = 0;
 
   // device state
@@ -196,6 +198,28 @@ cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c
   return cudaGetLastError();
 }
 
+template <int RANK, int TZ>
+cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = spread_ws_smem_bytes<RANK>(p->bin);
+#define WS_CASE(NS)                                                                              \
+  case NS: {                                                                                     \
+    auto k = spread_ws_f32_kernel<NS, RANK, TZ>;                                                 \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw);                 \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    WS_CASE(2) WS_CASE(3) WS_CASE(4) WS_CASE(5) WS_CASE(6) WS_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef WS_CASE
+  return cudaGetLastError();
+}
+
 template <int RANK>
 cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
@@ -222,7 +246,16 @@ cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* f
 template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->spread_method == 2) {
+  if (p->spread_method == 3) {
+    cudaError_t e;
+    const float2* cc = static_cast<const float2*>(c);
+    float2* ff = static_cast<float2*>(fw);
+    if (p->rank == 2) e = launch_spread_ws<2, 1>(p, ntr, cc, ff, st);
+    else if (p->bin[2] == 4) e = launch_spread_ws<3, 12>(p, ntr, cc, ff, st);
+    else if (p->bin[2] == 8) e = launch_spread_ws<3, 16>(p, ntr, cc, ff, st);
+    else e = cudaErrorInvalidValue;
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread ws launch: %s", cudaGetErrorString(e));
+  } else if (p->spread_method == 2) {
     cudaError_t e = p->rank == 2
         ? launch_spread_tile<2, 1>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st)
         : launch_spread_tile<3, kSpreadWarps3D>(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st);
@@ -370,6 +403,11 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.rank = rank;
   bg.rounding = 0;
   for (int d = 0; d < 3; ++d) { bg.nf[d] = p->nf[d]; bg.bin[d] = p->bin[d]; bg.nbins[d] = p->nbins[d]; }
+  bg.ws = p->ws ? 1 : 0;
+  bg.WX = p->bin[0] / 2 + 3;
+  bg.WY = p->bin[1] + 7;
+  bg.align_x = p->is_double ? 0 : 1;
+  const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY : 1);
 
   CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * p->nbtot, st));
   CUDA_OK(p, cudaMemsetAsync(p->range_flag(), 0, sizeof(int), st));
@@ -378,7 +416,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   const int check = p->opts.check_points_range && p->opts.points_range != B200NUFFT_RANGE_INFINITE;
   fold_key_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
       M, layout, static_cast<const F*>(x), static_cast<const F*>(y), static_cast<const F*>(z),
-      p->opts.points_range, check, lo, hi, bg, p->folded[0].as<F>(), p->folded[1].as<F>(),
+      p->opts.points_range, check, lo, hi, bg, static_cast<F>(p->kp.half_width), p->folded[0].as<F>(), p->folded[1].as<F>(),
       p->folded[2].as<F>(), p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
       p->range_flag());
   LAUNCH_OK(p);
@@ -387,7 +425,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   uint32_t* ks;
   int* vs;
   p->launches += radix_sort_pairs(p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->keys1.as<uint32_t>(),
-                                  p->vals1.as<int>(), M, ilog2_ceil(p->nbtot), p->hist.as<int>(),
+                                  p->vals1.as<int>(), M, ilog2_ceil(key_space), p->hist.as<int>(),
                                   p->scan_tmp(), &ks, &vs, st);
   LAUNCH_OK(p);
   p->idx = vs;
@@ -411,7 +449,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   p->launches++;
 
   const int align_x = (!p->is_double) ? 1 : 0;
-  stencil_record_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
+  stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
       M, rank, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns,
       static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
       p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
@@ -466,13 +504,20 @@ int create_impl(b200nufft_plan* p) {
 
   // ---- method + bin geometry ----
   const bool tile_ok = !p->is_double && ns <= 7 && p->rank >= 2;
-  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? 2 : 1) : p->opts.spread_method;
+  // auto: 2D -> window-sorted register-accumulating spreader (3); 3D -> plane-owner tile kernel (2)
+  // (measured on B200: cfg2 0.79 vs 1.13 ms per 8 coils; cfg3 3.2 ms tile vs >= 4.0 ms window-sorted)
+  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 3 : 2) : 1) : p->opts.spread_method;
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 2 : 1) : p->opts.interp_method;
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
   int def_bin[3] = {1, 1, 1};
   if (p->rank == 1) { def_bin[0] = 1024; }
   else if (p->rank == 2) { def_bin[0] = 32; def_bin[1] = 32; }
-  else { def_bin[0] = 16; def_bin[1] = 16; def_bin[2] = (p->type == 2) ? 8 : 2; }
+  else {
+    def_bin[0] = 16;
+    def_bin[1] = 16;
+    def_bin[2] = (p->type == 2) ? 2 : (p->spread_method == 3 ? 8 : 2);
+    if (p->type == 1 && p->spread_method == 3) def_bin[1] = 8;
+  }
   p->nbtot = 1;
   for (int d = 0; d < 3; ++d) {
     p->bin[d] = d < p->rank ? (p->opts.bin_dims[d] > 0 ? p->opts.bin_dims[d] : def_bin[d]) : 1;
@@ -480,13 +525,21 @@ int create_impl(b200nufft_plan* p) {
     p->nbtot *= p->nbins[d];
   }
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;
-  const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method == 2 : false;
+  const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
+  p->ws = uses_tile && p->type == 1 && p->spread_method == 3;
+  if (p->ws && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)
+    return set_err(p, B200NUFFT_INVALID_ARGUMENT, "window-sorted 3D spreader needs bin_dims[2] of 4 or 8");
+  if (p->ws && static_cast<int64_t>(p->nbtot) * (p->bin[0] / 2 + 3) * (p->bin[1] + 7) >= (int64_t(1) << 31)) {
+    p->ws = false;
+    p->spread_method = 2;
+  }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method == 2 : false;
   if (uses_tile || uses_tile_i) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
-    if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
+    if (uses_tile && p->spread_method == 3) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2>(p->bin) : spread_ws_smem_bytes<3>(p->bin));
+    else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
     if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)

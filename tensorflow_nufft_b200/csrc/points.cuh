@@ -47,6 +47,12 @@ struct BinGeom {
   int bin[3];
   int nbins[3];
   int rounding;  // 0: GPU rule floor+clamp; 1: CPU rule int() truncation (nbins = nf/bin+1)
+  // Window sort (type-1 tile spreader): key = bin * (WX*WY) + wy*WX + wx, where (wx, wy) is the
+  // position of the point's stencil window inside the bin's tile (x in pairs of cells). Points of
+  // a bin that share a window become adjacent, so the spreader can accumulate them in registers.
+  int ws;        // 0: key = bin only
+  int WX, WY;
+  int align_x;   // stencil x start aligned down to an even cell
 };
 
 template <typename F>
@@ -72,7 +78,7 @@ __device__ __forceinline__ int bin_of(F x, int bin_dim, int nbins, int rounding)
 template <typename F>
 __global__ void __launch_bounds__(256)
 fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __restrict__ p1,
-                const F* __restrict__ p2, int range, int check, F lo, F hi, BinGeom g,
+                const F* __restrict__ p2, int range, int check, F lo, F hi, BinGeom g, F half_width,
                 F* __restrict__ f0, F* __restrict__ f1, F* __restrict__ f2,
                 uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes,
                 int* __restrict__ range_flag) {
@@ -89,15 +95,28 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
     int bad = 0;
     int key = 0;
     int mul = 1;
+    int bd[3] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (d < g.rank) {
         if (check && !((x[d] > lo) && (x[d] < hi))) bad |= (1 << d);
         F xf = fold_rescale<F>(x[d], range, g.nf[d]);
         x[d] = xf;
-        key += mul * bin_of<F>(xf, g.bin[d], g.nbins[d], g.rounding);
+        bd[d] = bin_of<F>(xf, g.bin[d], g.nbins[d], g.rounding);
+        key += mul * bd[d];
         mul *= g.nbins[d];
       }
+    }
+    const int bin_key = key;
+    if (g.ws) {
+      const int i1x = static_cast<int>(ceil(sub_rn(x[0], half_width)));
+      const int x0 = i1x - (g.align_x ? (i1x & 1) : 0);
+      int wx = (x0 - (bd[0] * g.bin[0] - 4)) >> 1;
+      const int i1y = static_cast<int>(ceil(sub_rn(x[1], half_width)));
+      int wy = i1y - (bd[1] * g.bin[1] - 4);
+      wx = wx < 0 ? 0 : (wx >= g.WX ? g.WX - 1 : wx);
+      wy = wy < 0 ? 0 : (wy >= g.WY ? g.WY - 1 : wy);
+      key = key * (g.WX * g.WY) + wy * g.WX + wx;
     }
     f0[i] = x[0];
     if (g.rank > 1) f1[i] = x[1];
@@ -107,9 +126,9 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
     // Warp-aggregated histogram: one atomic per distinct bin per warp (hot bins, e.g. the
     // k-space centre of a radial trajectory, would otherwise serialise).
     const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, key);
+    const unsigned peers = __match_any_sync(active, bin_key);
     const int leader = __ffs(peers) - 1;
-    if ((threadIdx.x & 31) == leader) atomicAdd(&bin_sizes[key], __popc(peers));
+    if ((threadIdx.x & 31) == leader) atomicAdd(&bin_sizes[bin_key], __popc(peers));
     if (bad) atomicOr(range_flag, bad);
   }
 }
@@ -172,7 +191,11 @@ __device__ __forceinline__ F es_eval(F x, F beta, F c, F half_width) {
   double a = 1.0 - static_cast<double>(t);
   a = a < 0.0 ? 0.0 : a;
   F e = static_cast<F>(static_cast<double>(beta) * sqrt(a));
+#ifdef B200NUFFT_FAST_EXP
+  F k = exp(e);                                   // FloatType exp (<= 2 ulp for float)
+#else
   F k = static_cast<F>(exp(static_cast<double>(e)));
+#endif
   return (fabs(x) >= half_width) ? F(0) : k;
 }
 
@@ -182,47 +205,33 @@ __device__ __forceinline__ F es_eval(F x, F beta, F c, F half_width) {
 //     wx[shift + k] = phi(x1 + k), k < ns, zero elsewhere (PX >= ns + 1)
 //     wy[k] = phi(y1 + k), wz[k] = phi(z1 + k), k < ns, zero padded
 // with i1 = ceil(x - ns/2), x1 = (F)i1 - x  (nufft_plan.cc:1187-1193).
+// One thread per WEIGHT (g = j*R + k): no loops, fully coalesced record writes, and the double
+// precision sqrt/exp work is spread evenly over the lanes.
 template <typename F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288)
 stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F* __restrict__ f0,
                       const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
                       int align_x, int R, int PX, int PY, int4* __restrict__ start, F* __restrict__ wrec) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < M; j += stride) {
+  // block = (R, points per block): k = threadIdx.x, no integer division anywhere.
+  const int k = threadIdx.x;
+  const int64_t jstride = static_cast<int64_t>(gridDim.x) * blockDim.y;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.y + threadIdx.y; j < M; j += jstride) {
+    const int64_t g = j * R + k;
+    const int d = k < PX ? 0 : (k < PX + PY ? 1 : 2);
+    const int tap = d == 0 ? k : (d == 1 ? k - PX : k - PX - PY);
     const int i = idx[j];
-    int4 st = make_int4(0, 0, 0, 0);
-    F* w = wrec + j * R;
-    {
-      const F x = f0[i];
-      const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
-      const F x1 = sub_rn(static_cast<F>(i1), x);
-      const int shift = align_x ? (i1 & 1) : 0;
-      st.x = i1 - shift;
-      st.w = shift;
-      for (int k = 0; k < PX; ++k) {
-        const int t = k - shift;
-        w[k] = (t >= 0 && t < ns) ? es_eval<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
-      }
-      w += PX;
+    const F x = d == 0 ? f0[i] : (d == 1 ? f1[i] : f2[i]);
+    const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
+    const F x1 = sub_rn(static_cast<F>(i1), x);
+    const int shift = (d == 0 && align_x) ? (i1 & 1) : 0;
+    const int t = tap - shift;
+    wrec[g] = (t >= 0 && t < ns) ? es_eval<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
+    if (k == 0) {
+      int4 st = make_int4(i1 - shift, 0, 0, shift);
+      if (rank > 1) st.y = static_cast<int>(ceil(sub_rn(f1[i], half_width)));
+      if (rank > 2) st.z = static_cast<int>(ceil(sub_rn(f2[i], half_width)));
+      start[j] = st;
     }
-    if (rank > 1) {
-      const F y = f1[i];
-      const int i1 = static_cast<int>(ceil(sub_rn(y, half_width)));
-      const F y1 = sub_rn(static_cast<F>(i1), y);
-      st.y = i1;
-      for (int k = 0; k < PY; ++k)
-        w[k] = (k < ns) ? es_eval<F>(add_rn(y1, static_cast<F>(k)), beta, c, half_width) : F(0);
-      w += PY;
-    }
-    if (rank > 2) {
-      const F z = f2[i];
-      const int i1 = static_cast<int>(ceil(sub_rn(z, half_width)));
-      const F z1 = sub_rn(static_cast<F>(i1), z);
-      st.z = i1;
-      for (int k = 0; k < PY; ++k)
-        w[k] = (k < ns) ? es_eval<F>(add_rn(z1, static_cast<F>(k)), beta, c, half_width) : F(0);
-    }
-    start[j] = st;
   }
 }
 

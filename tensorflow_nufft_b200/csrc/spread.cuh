@@ -94,9 +94,12 @@ spread_global_kernel(int64_t M, int ntr, GridGeom g, int ns, int R, int PX, int 
 // 16 cells, stage record stride = 4 mod 32 words).
 // ---------------------------------------------------------------------------------------------
 template <int RANK> struct StageRec {
-  // words: [0] tile offset (cells) or -1, [1] tile z of the stencil start, [2] Re c, [3] Im c,
-  //        [4..11] wx, [12..19] wy, [20..27] wz (3D)
-  static constexpr int kWords = RANK == 3 ? 28 : 20;
+  // spread: words [0..7] wx, [8..23] cw[r] = {Re c * wy[r], Im c * wy[r]}, [24] tile offset (cells)
+  //         or -1, [25] tile z of the stencil start, [26..27] pad, [28..35] wz (3D)
+  // interp: words [0..7] wx, [8..15] wy, [16..23] wz, [24] tile offset or -1
+  // Per-point broadcast data is read with 64/32-bit loads: a 128-bit shared load costs 4
+  // wavefronts (one per quarter warp) even when all lanes share addresses.
+  static constexpr int kWords = RANK == 3 ? 44 : 36;   // stride = 12 / 4 mod 32: conflict-free staging
 };
 
 template <int NS, int RANK, int WPT>
@@ -173,9 +176,15 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                         (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
       if (fits) { off = (rz * TY + ry) * TX + rx; tz = rz; }
     }
-    rec4[0] = make_float4(__int_as_float(off), __int_as_float(tz), c_n.x, c_n.y);
-#pragma unroll
-    for (int k = 0; k < C4; ++k) rec4[1 + k] = w4[k];
+    rec4[0] = w4[0];
+    rec4[1] = w4[1];
+    const float cre = c_n.x, cim = c_n.y;
+    rec4[2] = make_float4(cre * w4[2].x, cim * w4[2].x, cre * w4[2].y, cim * w4[2].y);
+    rec4[3] = make_float4(cre * w4[2].z, cim * w4[2].z, cre * w4[2].w, cim * w4[2].w);
+    rec4[4] = make_float4(cre * w4[3].x, cim * w4[3].x, cre * w4[3].y, cim * w4[3].y);
+    rec4[5] = make_float4(cre * w4[3].z, cim * w4[3].z, cre * w4[3].w, cim * w4[3].w);
+    rec4[6] = make_float4(__int_as_float(off), __int_as_float(tz), 0.f, 0.f);
+    if (RANK > 2) { rec4[7] = w4[C4 - 2]; rec4[8] = w4[C4 - 1]; }
   };
   if (warp == 0) {
     if (lane < np) id_n2 = idx[p0 + lane];
@@ -190,30 +199,38 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
 
     const float* sbuf = stage + (bb % NBUF) * BS * SW;
     const int cnt = min(BS, np - bb * BS);
+    // Inner loop, software-pipelined by hand: the small per-point loads (header, wx pair, wy) of
+    // point p+1 are issued before the tile read-modify-write of point p, so that the dependent
+    // chain per point is only LDS.128 -> FFMA -> STS.128.
+    const int rr = row_ok ? r : 0;
+    float2 of = *reinterpret_cast<const float2*>(sbuf + 24);
+    float2 wx = *reinterpret_cast<const float2*>(sbuf + 2 * q);
+    float2 cw = *reinterpret_cast<const float2*>(sbuf + 8 + 2 * rr);
     for (int p = 0; p < cnt; ++p) {
       const float* rec = sbuf + p * SW;
-      const float4 hdr = *reinterpret_cast<const float4*>(rec);
-      const int off = __float_as_int(hdr.x);
+      const float2 of_c = of, wx_c = wx, cw_c = cw;
+      if (p + 1 < cnt) {
+        const float* nxt = rec + SW;
+        of = *reinterpret_cast<const float2*>(nxt + 24);
+        wx = *reinterpret_cast<const float2*>(nxt + 2 * q);
+        cw = *reinterpret_cast<const float2*>(nxt + 8 + 2 * rr);
+      }
+      const int off = __float_as_int(of_c.x);
       if (off >= 0) {
+        const float4 cx = make_float4(cw_c.x * wx_c.x, cw_c.y * wx_c.x, cw_c.x * wx_c.y, cw_c.y * wx_c.y);
         if (RANK == 2) {
           if (row_ok) {
-            const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
-            const float wy = rec[12 + r];
-            const float a = hdr.z * wy, bq = hdr.w * wy;
             float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off);
             float4 v = *ptr;
-            v.x += a * wx.x; v.y += bq * wx.x; v.z += a * wx.y; v.w += bq * wx.y;
+            v.x += cx.x; v.y += cx.y; v.z += cx.z; v.w += cx.w;
             *ptr = v;
           }
         } else {
-          const int tz = __float_as_int(hdr.y);
+          const int tz = __float_as_int(of_c.y);
           // first stencil plane owned by this warp: (tz + dz) % WPT == warp
           int dz0 = (warp - tz) % WPT;
           dz0 = dz0 < 0 ? dz0 + WPT : dz0;
           if (row_ok && dz0 < NS) {
-            const float2 wx = *reinterpret_cast<const float2*>(rec + 4 + 2 * q);
-            const float wy = rec[12 + r];
-            const float4 cx = make_float4(hdr.z * wx.x, hdr.w * wx.x, hdr.z * wx.y, hdr.w * wx.y);
             float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off);
             constexpr int KMAX = (NS + WPT - 1) / WPT;
             float4 v[KMAX];
@@ -223,7 +240,7 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
               const int dz = dz0 + k * WPT;
               if (dz < NS) {
                 v[k] = ptr[dz * zstride4];
-                w[k] = wy * rec[20 + dz];
+                w[k] = rec[28 + dz];
               }
             }
 #pragma unroll

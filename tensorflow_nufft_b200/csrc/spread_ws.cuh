@@ -1,0 +1,248 @@
+// spread_ws.cuh -- window-sorted type-1 spreader (complex64, ns <= 7, rank 2 or 3).
+//
+// Same sums as spread.cuh (reference: SpreadSubproblem{2,3}DKernel nufft_plan.cu.cc:790-878,
+// 1404-1510), different schedule. The bin-sort key is refined to (bin, stencil window) so that the
+// points of a subproblem arrive grouped by the position of their stencil inside the bin's tile.
+// One warp owns one tile. Lanes are laid over the stencil (row r = lane / QX, cell pair
+// q = lane % QX); for a RUN of points with the same window every lane's target cells are the same,
+// so the run is accumulated in REGISTERS (4 FFMA per point per lane in 2D, 28 in 3D) and the
+// shared-memory tile is touched once per run (LDS.128 / FADD / STS.128) instead of once per point.
+// In 3D a lane keeps the whole z-column of the tile under its (x pair, y row) in registers, the z
+// start of each point selects one of TZ-NS+1 unrolled update variants (warp-uniform switch).
+// Shared-memory traffic per point drops from 8 (2D) / 56 (3D) read-modify-write wavefronts to
+// 8 / run-length (2D) and 8*TZ / run-length (3D); no atomics in shared memory; tile flushed to the
+// fine grid with REDG.E.ADD.F32x4.
+#pragma once
+#include "dev_common.cuh"
+#include "spread.cuh"
+
+namespace b200 {
+
+template <int RANK> struct WsRec {
+  // words: [0..7]   wx[8]
+  //        [8..23]  cw[r] = {Re c * wy[r], Im c * wy[r]}   r < 8
+  //        [24]     off2d (cells) of the stencil window, or -1 for a dropped point
+  //        [25]     tz (3D: tile z of the stencil start)
+  //        [26]     flag: 1 if this point opens a new run (window differs from the previous point)
+  //        [27]     pad
+  //        [28..35] wz[8]                                  (3D)
+  // 128-bit shared loads always cost 4 wavefronts (one per quarter warp) even when lanes share
+  // addresses, so the per-point broadcast data is read with 64/32-bit loads (1 wavefront each).
+  static constexpr int kStride = RANK == 3 ? 44 : 36;   // = 12 / 4 mod 32 words: conflict-free staging
+};
+
+template <int NS, int TZ, int TZ0>
+struct ColumnUpdate {
+  // v[TZ0 + dz] += wz[dz] * cx  for dz < NS, with compile-time register indices
+  __device__ static __forceinline__ void run(float4 (&v)[TZ], const float (&wz)[8], const float4& cx) {
+#pragma unroll
+    for (int dz = 0; dz < NS; ++dz) {
+      if (TZ0 + dz < TZ) {
+        v[TZ0 + dz].x += wz[dz] * cx.x;
+        v[TZ0 + dz].y += wz[dz] * cx.y;
+        v[TZ0 + dz].z += wz[dz] * cx.z;
+        v[TZ0 + dz].w += wz[dz] * cx.w;
+      }
+    }
+  }
+};
+
+template <int NS, int TZ, int K>
+struct ColumnDispatch {
+  __device__ static __forceinline__ void run(int tz, float4 (&v)[TZ], const float (&wz)[8], const float4& cx) {
+    if (tz == K) ColumnUpdate<NS, TZ, K>::run(v, wz, cx);
+    else ColumnDispatch<NS, TZ, K - 1>::run(tz, v, wz, cx);
+  }
+};
+template <int NS, int TZ>
+struct ColumnDispatch<NS, TZ, -1> {
+  __device__ static __forceinline__ void run(int, float4 (&)[TZ], const float (&)[8], const float4&) {}
+};
+
+// TZ = bin_z + 8 for RANK 3 (compile time: the z-column lives in registers), 1 for RANK 2.
+template <int NS, int RANK, int TZ>
+__global__ void __launch_bounds__(32)
+spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
+                     const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                     const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][2*RANK]*/,
+                     const float2* __restrict__ c, float2* __restrict__ fw) {
+  constexpr int QX = (NS + 2) / 2;
+  static_assert(QX * NS <= 32, "stencil slab must fit one warp");
+  constexpr int C4 = 2 * RANK;
+  constexpr int SW = WsRec<RANK>::kStride;
+  constexpr int BS = 32;
+  extern __shared__ float4 smem4[];
+
+  const int s = blockIdx.x;
+  if (s >= *sub_total) return;
+  const int lane = threadIdx.x;
+  const int t = blockIdx.y;
+  const int4 sd = sub_desc[s];
+  const int b = sd.x, p0 = sd.y, np = sd.z;
+
+  const int TX = g.bin[0] + 8, TY = g.bin[1] + 8;
+  const int bx = b % g.nbins[0];
+  const int by = (b / g.nbins[0]) % g.nbins[1];
+  const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
+  const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
+  const int plane = TX * TY;
+  const int ncell = plane * TZ;
+  float4* tile4 = smem4;
+  float2* tile = reinterpret_cast<float2*>(tile4);
+  float* stage = reinterpret_cast<float*>(smem4 + ncell / 2);   // [BS][SW]
+
+  for (int i = lane; i < ncell / 2; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int q = lane % QX;
+  const int r = lane / QX;
+  const bool row_ok = r < NS;
+  const int rr = row_ok ? r : 0;
+  const int lane_off = rr * TX + 2 * q;
+  const int zstride4 = plane / 2;
+
+  const float2* ct = c + static_cast<int64_t>(t) * M;
+  float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+
+  // ---- register prefetch of this lane's point of the next batch ----
+  float4 w4[C4];
+  int4 st_n = make_int4(0, 0, 0, 0);
+  float2 c_n = make_float2(0.f, 0.f);
+  int id_n2 = 0;
+  auto fetch = [&](int bb) {
+    const int pl = bb * BS + lane;
+    if (pl < np) {
+      const int64_t j = p0 + pl;
+#pragma unroll
+      for (int k = 0; k < C4; ++k) w4[k] = wrec4[j * C4 + k];
+      st_n = start[j];
+      c_n = ct[id_n2];
+    }
+    const int pl2 = (bb + 1) * BS + lane;
+    if (pl2 < np) id_n2 = idx[p0 + pl2];
+  };
+  int last_off = -2;   // window of the last point of the previous batch (forces a flag at the start)
+  auto stage_write = [&](int bb) {
+    const int pl = bb * BS + lane;
+    float4* rec4 = reinterpret_cast<float4*>(stage + lane * SW);
+    int off = -1, tz = 0;
+    if (pl < np) {
+      const int rx = st_n.x - ox, ry = st_n.y - oy, rz = RANK > 2 ? st_n.z - oz : 0;
+      // Memory safety for coordinates outside the declared points_range: the stencil does not lie
+      // in this bin's tile and the point is dropped (the reference's behaviour is undefined there).
+      const bool fits = rx >= 0 && rx + 2 * QX <= TX && ry >= 0 && ry + NS <= TY &&
+                        (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
+      if (fits) { off = ry * TX + rx; tz = rz; }
+    }
+    // run flag: compare with the previous point's window (previous lane, or the last point of the
+    // previous batch for lane 0)
+    const int prev = __shfl_up_sync(0xffffffffu, off, 1);
+    const int flag = (lane == 0 ? (off != last_off) : (off != prev)) ? 1 : 0;
+    last_off = __shfl_sync(0xffffffffu, off, 31);
+    rec4[0] = w4[0];
+    rec4[1] = w4[1];
+    const float cre = c_n.x, cim = c_n.y;
+    rec4[2] = make_float4(cre * w4[2].x, cim * w4[2].x, cre * w4[2].y, cim * w4[2].y);
+    rec4[3] = make_float4(cre * w4[2].z, cim * w4[2].z, cre * w4[2].w, cim * w4[2].w);
+    rec4[4] = make_float4(cre * w4[3].x, cim * w4[3].x, cre * w4[3].y, cim * w4[3].y);
+    rec4[5] = make_float4(cre * w4[3].z, cim * w4[3].z, cre * w4[3].w, cim * w4[3].w);
+    rec4[6] = make_float4(__int_as_float(off), __int_as_float(tz), __int_as_float(flag), 0.f);
+    if (RANK > 2) { rec4[7] = w4[C4 - 2]; rec4[8] = w4[C4 - 1]; }
+  };
+  if (lane < np) id_n2 = idx[p0 + lane];
+  fetch(0);
+
+  // ---- run accumulator ----
+  float4 v[TZ];
+#pragma unroll
+  for (int z = 0; z < TZ; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = -1;   // 2D window offset (cells) of the open run, -1 = none
+  int zlo = TZ, zhi = 0;   // planes touched by the open run (warp-uniform)
+  auto flush_run = [&]() {
+    if (cur >= 0 && row_ok) {
+      float4* ptr = reinterpret_cast<float4*>(tile + cur + lane_off);
+#pragma unroll
+      for (int z = 0; z < TZ; ++z) {
+        if (RANK == 2 || (z >= zlo && z < zhi)) {
+          float4 tv = ptr[z * zstride4];
+          tv.x += v[z].x; tv.y += v[z].y; tv.z += v[z].z; tv.w += v[z].w;
+          ptr[z * zstride4] = tv;
+        }
+      }
+    }
+#pragma unroll
+    for (int z = 0; z < TZ; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+    zlo = TZ;
+    zhi = 0;
+    __syncwarp();
+  };
+
+  const int nbatch = (np + BS - 1) / BS;
+  for (int bb = 0; bb < nbatch; ++bb) {
+    stage_write(bb);
+    __syncwarp();
+    if (bb + 1 < nbatch) fetch(bb + 1);
+
+    const int cnt = min(BS, np - bb * BS);
+    // The stage holds BS + 1 records so that the prefetch of point p + 1 never needs a guard.
+    float2 wx = *reinterpret_cast<const float2*>(stage + 2 * q);
+    float2 cw = *reinterpret_cast<const float2*>(stage + 8 + 2 * rr);
+    float2 of = *reinterpret_cast<const float2*>(stage + 24);
+    int fl = __float_as_int(stage[26]);
+#pragma unroll 2
+    for (int p = 0; p < cnt; ++p) {
+      const float* rec = stage + p * SW;
+      const float2 wx_c = wx, cw_c = cw, of_c = of;
+      const int fl_c = fl;
+      wx = *reinterpret_cast<const float2*>(rec + SW + 2 * q);
+      cw = *reinterpret_cast<const float2*>(rec + SW + 8 + 2 * rr);
+      of = *reinterpret_cast<const float2*>(rec + SW + 24);
+      fl = __float_as_int(rec[SW + 26]);
+      if (fl_c) {              // warp-uniform
+        flush_run();
+        cur = __float_as_int(of_c.x);
+      }
+      // dropped points carry cur = -1 and are accumulated into registers that are never stored
+      const float4 cx = make_float4(cw_c.x * wx_c.x, cw_c.y * wx_c.x, cw_c.x * wx_c.y, cw_c.y * wx_c.y);
+      if constexpr (RANK == 2) {
+        v[0].x += cx.x; v[0].y += cx.y; v[0].z += cx.z; v[0].w += cx.w;
+      } else {
+        float wz[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t2 = *reinterpret_cast<const float2*>(rec + 28 + 2 * k);
+          wz[2 * k] = t2.x;
+          wz[2 * k + 1] = t2.y;
+        }
+        const int tz = __float_as_int(of_c.y);
+        zlo = min(zlo, tz);
+        zhi = max(zhi, tz + NS);
+        ColumnDispatch<NS, TZ, TZ - NS>::run(tz, v, wz, cx);
+      }
+    }
+    __syncwarp();
+  }
+  flush_run();
+
+  // Flush the tile: two complex cells per REDG.ADD.F32x4; periodic wrap; zero pairs skipped.
+  const int TXH = TX / 2;
+  for (int i = lane; i < ncell / 2; i += 32) {
+    const float4 tv = tile4[i];
+    if (tv.x == 0.f && tv.y == 0.f && tv.z == 0.f && tv.w == 0.f) continue;
+    const int ix = i % TXH;
+    const int iy = (i / TXH) % TY;
+    const int iz = i / (TXH * TY);
+    const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
+    const int gy = mod_idx(oy + iy, g.nf[1]);
+    const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
+    float2* dst = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
+    red_add(reinterpret_cast<float4*>(dst), tv);
+  }
+}
+
+template <int RANK>
+inline size_t spread_ws_smem_bytes(const int* bin) {
+  const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
+  return ncell * sizeof(float2) + 33 * WsRec<RANK>::kStride * sizeof(float);
+}
+
+}  // namespace b200

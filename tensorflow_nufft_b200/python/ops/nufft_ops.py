@@ -150,6 +150,10 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
     raise RuntimeError("tensorflow_nufft_b200 needs a CUDA device; there is no CPU fallback")
   host_io = not source.is_cuda
   device = source.device if source.is_cuda else torch.device("cuda", torch.cuda.current_device())
+  if (host_io and op_type == "nufft" and not outer and num_transforms > _HOST_CHUNK and
+      all(d != 0 for d in target_shape) and source.is_contiguous()):
+    return _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, options,
+                               num_transforms, num_points, target_shape, device, engine_kwargs)
   src = source.to(device, non_blocking=True) if host_io else source
   pts = points.to(device, non_blocking=True) if not points.is_cuda else points
   if pts.device != device:
@@ -231,6 +235,90 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
   tgt = tgt.permute(inv + list(range(nb, nb + len(target_elem)))).contiguous()
   tgt = tgt.reshape(target_shape)
   return _to_host(tgt) if host_io else tgt
+
+
+_HOST_CHUNK = 8   # transforms per pipelined chunk (= the engine's batch size)
+
+
+def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, options, num_transforms,
+                        num_points, target_shape, device, engine_kwargs):
+  """Host-resident inputs, many transforms sharing one point set: the coils are streamed through
+  the GPU in chunks of _HOST_CHUNK with the H2D copy of chunk k+1, the transform of chunk k and
+  the D2H copy of chunk k-1 overlapped on three CUDA streams (the PCIe copies dominate: 8 bytes
+  per point-transform each way)."""
+  dev_index = device.index if device.index is not None else torch.cuda.current_device()
+  n_coeffs = 1
+  for g in grid_shape:
+    n_coeffs *= g
+  src_elems = num_points if ttype == 1 else n_coeffs
+  tgt_elems = n_coeffs if ttype == 1 else num_points
+  T = num_transforms
+  src_flat = source.reshape(T, src_elems)
+  if not src_flat.is_pinned():
+    src_flat = src_flat.pin_memory()
+  out = torch.empty((T, tgt_elems), dtype=source.dtype, pin_memory=True)
+  opt_kwargs = dict(_ENGINE_DEFAULTS)
+  opt_kwargs.update((options or nufft_options.Options()).to_engine_kwargs())
+  if engine_kwargs:
+    opt_kwargs.update(engine_kwargs)
+  dcode = _lib.COMPLEX64 if source.dtype == torch.complex64 else _lib.COMPLEX128
+  sign = -1 if fft_direction == "forward" else 1
+  chunk = _HOST_CHUNK
+  with torch.cuda.device(dev_index):
+    main = torch.cuda.current_stream()
+    copy_in, copy_out = _side_streams(dev_index)
+    pts = points.to(device, non_blocking=True).reshape(num_points, -1)
+    plan = _get_plan((ttype, tuple(reversed(grid_shape)), sign, chunk, _op_tol(tol), dcode, dev_index), opt_kwargs)
+    rem = T % chunk
+    plan_rem = None
+    if rem:
+      plan_rem = _get_plan((ttype, tuple(reversed(grid_shape)), sign, rem, _op_tol(tol), dcode, dev_index), opt_kwargs)
+    plan.set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
+    if plan_rem is not None:
+      plan_rem.set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
+    d_in = [torch.empty((chunk, src_elems), dtype=source.dtype, device=device) for _ in range(2)]
+    d_out = [torch.empty((chunk, tgt_elems), dtype=source.dtype, device=device) for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    out_ready = [torch.cuda.Event() for _ in range(2)]
+    out_free = [torch.cuda.Event() for _ in range(2)]
+    copy_in.wait_stream(main)
+    nchunks = (T + chunk - 1) // chunk
+    for k in range(nchunks):
+      b0 = k * chunk
+      n = min(chunk, T - b0)
+      s = k & 1
+      with torch.cuda.stream(copy_in):
+        if k >= 2:
+          copy_in.wait_event(in_free[s])
+        d_in[s][:n].copy_(src_flat[b0:b0 + n], non_blocking=True)
+        in_ready[s].record(copy_in)
+      main.wait_event(in_ready[s])
+      if k >= 2:
+        main.wait_event(out_free[s])
+      pl = plan if n == chunk else plan_rem
+      if ttype == 1:
+        pl.execute(d_in[s].data_ptr(), d_out[s].data_ptr(), main.cuda_stream)
+      else:
+        pl.execute(d_out[s].data_ptr(), d_in[s].data_ptr(), main.cuda_stream)
+      in_free[s].record(main)
+      out_ready[s].record(main)
+      with torch.cuda.stream(copy_out):
+        copy_out.wait_event(out_ready[s])
+        out[b0:b0 + n].copy_(d_out[s][:n], non_blocking=True)
+        out_free[s].record(copy_out)
+    main.wait_stream(copy_out)
+    main.synchronize()
+  return out.reshape(target_shape)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev_index):
+  if dev_index not in _SIDE_STREAMS:
+    _SIDE_STREAMS[dev_index] = (torch.cuda.Stream(device=dev_index), torch.cuda.Stream(device=dev_index))
+  return _SIDE_STREAMS[dev_index]
 
 
 def _sum_to_shape(x, shape):

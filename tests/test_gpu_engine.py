@@ -221,9 +221,37 @@ def test_tile_and_global_kernels_agree(rank):
   res = {}
   for ttype in (1, 2):
     src = H.random_complex((2, M) if ttype == 1 else (2,) + grid, 42)
-    for meth in (1, 2):
+    for meth in (1, 2, 3):
       out = nufft_ops._run_op(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid, f"type_{ttype}",
                               "forward", 1e-6, None, "nufft",
-                              engine_kwargs={"spread_method": meth, "interp_method": meth})
+                              engine_kwargs={"spread_method": meth, "interp_method": min(meth, 2)})
       res[(ttype, meth)] = out.cpu().numpy()
     assert H.rel_l2(res[(ttype, 2)], res[(ttype, 1)]) < 5e-7
+    assert H.rel_l2(res[(ttype, 3)], res[(ttype, 1)]) < 5e-7
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_window_sorted_plan_keeps_reference_bins(rank):
+  """Type-1 plans refine the sort key to (bin, stencil window). The bin offsets and sizes must
+  still be the reference's bit-exactly, and every bin must hold exactly the reference's point set
+  (the order inside a bin is by window, then by point index)."""
+  from tensorflow_nufft_b200 import _lib
+  grid = (128, 96) if rank == 2 else (32, 48, 40)
+  pts = H.uniform_points(120000, rank, 77)
+  pts[:2000] = H.radial_points(20, 100)[:, :rank] if rank == 2 else pts[:2000]
+  plan = _lib.Plan(1, tuple(reversed(grid)), -1, 1, 1e-6, _lib.COMPLEX64)
+  dp = torch.from_numpy(pts).cuda()
+  plan.set_points_interleaved(pts.shape[0], dp.data_ptr(), None)
+  torch.cuda.synchronize()
+  idx, start, sizes = plan.sort_arrays()
+  info = plan.info()
+  fine = [info.fine_dims[d] for d in range(rank)]
+  bins = [info.bin_dims[d] for d in range(rank)]
+  folded = np.stack([H.fold_rescale_np(pts[:, rank - 1 - d], fine[d]) for d in range(rank)])
+  widx, wstart, wsizes = H.binsort_np(folded, fine, bins, 0)
+  assert np.array_equal(start, wstart) and np.array_equal(sizes, wsizes)
+  assert sorted(idx.tolist()) == list(range(pts.shape[0]))
+  ends = wstart + wsizes
+  for b in np.nonzero(wsizes)[0][:2000]:
+    assert np.array_equal(np.sort(idx[wstart[b]:ends[b]]), widx[wstart[b]:ends[b]])
+  plan.close()
