@@ -10,6 +10,7 @@
 //                            subproblem, lanes laid over the stencil (row = lane / QX, cell pair =
 //                            lane % QX): 128-bit conflict-free shared loads, butterfly reduction.
 #pragma once
+#include <cuda.h>
 #include <cuda_pipeline.h>
 
 #include "dev_common.cuh"
@@ -53,8 +54,49 @@ interp_global_kernel(int64_t M, int ntr, GridGeom g, int ns, int R, int PX, int 
   }
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers, raw PTX for sm_100a ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// One box of the fine grid -> shared memory. Coordinates are in elements of the tensor map
+// (float32; innermost dim = 2 * nf0 interleaved re/im), fastest dimension first.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // One CTA (WARPS warps) per (subproblem, transform). The (bin + halo) tile is copied into shared
-// memory with 16-byte cp.async (LDGSTS) copies, then each warp takes batches of 32 points: lane l
+// memory by ONE TMA box copy (cp.async.bulk.tensor, completion on an mbarrier) when the tile lies
+// inside the grid, or with 16-byte cp.async (LDGSTS) copies with index wrapping when it straddles
+// the periodic boundary (TMA zero-fills out-of-bounds, it does not wrap). Then each warp takes
+// batches of 32 points: lane l
 // prefetches the record of its point of the NEXT batch (weights, start, point id) while the warp
 // gathers the current batch from the tile; records are staged per warp in shared memory
 // ({tile offset, wx[8], wy[8], wz[8]}), results are reduced by butterfly shuffles and scattered to
@@ -64,11 +106,12 @@ __global__ void __launch_bounds__(WARPS * 32)
 interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                        const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                        const int4* __restrict__ start, const float4* __restrict__ wrec4,
-                       const float2* __restrict__ fw, float2* __restrict__ c) {
+                       const float2* __restrict__ fw, float2* __restrict__ c,
+                       const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int QX = (NS + 2) / 2;
   constexpr int C4 = 2 * RANK;
   constexpr int SW = StageRec<RANK>::kWords;
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
@@ -88,6 +131,7 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   float4* tile4 = smem4;
   const float2* tile = reinterpret_cast<const float2*>(tile4);
   float* stage = reinterpret_cast<float*>(smem4 + ncell / 2) + warp * 32 * SW;   // per warp [32][SW]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem4 + ncell / 2) + WARPS * 32 * SW);
 
   const float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
   float2* ct = c + static_cast<int64_t>(t) * M;
@@ -108,21 +152,35 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   };
   fetch(warp * 32);
 
-  // Stage the tile (two cells per 16-byte async copy; nf and the tile origin are even so a pair
-  // never straddles the periodic boundary).
-  for (int i = tid; i < ncell / 2; i += WARPS * 32) {
-    const int ix = i % TXH;
-    const int iy = (i / TXH) % TY;
-    const int iz = i / (TXH * TY);
-    const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
-    const int gy = mod_idx(oy + iy, g.nf[1]);
-    const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
-    const float2* src = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
-    __pipeline_memcpy_async(&tile4[i], src, 16);
+  const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
+                        (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]));
+  if (interior) {
+    // TMA: one elected thread arms the mbarrier with the tile's byte count and issues the box copy.
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, static_cast<uint32_t>(ncell * sizeof(float2)));
+      if (RANK == 2) tma_load_3d(tile4, &tmap, bar, 2 * ox, oy, t);
+      else tma_load_4d(tile4, &tmap, bar, 2 * ox, oy, oz, t);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    // Stage the tile (two cells per 16-byte async copy; nf and the tile origin are even so a pair
+    // never straddles the periodic boundary).
+    for (int i = tid; i < ncell / 2; i += WARPS * 32) {
+      const int ix = i % TXH;
+      const int iy = (i / TXH) % TY;
+      const int iz = i / (TXH * TY);
+      const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
+      const int gy = mod_idx(oy + iy, g.nf[1]);
+      const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
+      const float2* src = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
+      __pipeline_memcpy_async(&tile4[i], src, 16);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
   }
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
-  __syncthreads();
 
   const int q = lane % QX;
   const int r = lane / QX;
@@ -235,7 +293,7 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
 template <int RANK, int WARPS>
 inline size_t interp_tile_smem_bytes(const int* bin) {
   const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
-  return ncell * sizeof(float2) + static_cast<size_t>(WARPS) * 32 * StageRec<RANK>::kWords * sizeof(float);
+  return ncell * sizeof(float2) + static_cast<size_t>(WARPS) * 32 * StageRec<RANK>::kWords * sizeof(float) + 16;
 }
 
 }  // namespace b200

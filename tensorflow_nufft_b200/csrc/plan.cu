@@ -3,6 +3,7 @@
 // structure: everything is stream-ordered, the cuFFT plan and all buffers live in the plan (so a
 // cached plan costs nothing per call), no host synchronisation in set_points / execute, the
 // stencil records are precomputed once per point set and reused by every transform and execute.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cufft.h>
 
@@ -73,6 +74,10 @@ struct b200nufft_plan {
   int PX = 8, PY = 8, R = 8;
   int num_threads_compat = 1;
   int spread_method = 1, interp_method = 1;
+  CUtensorMap tmap;        // TMA descriptor of the fine grid (type-2 tile interpolator)
+  const void* tmap_ptr = nullptr;
+  int tmap_batch = 0;
+  bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   size_t tile_smem = 0;
 
@@ -220,9 +225,56 @@ cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, 
   return cudaGetLastError();
 }
 
+// Builds (or reuses) the TMA tensor map of a fine-grid batch [ntr][nf2][nf1][2*nf0] float32 with a
+// box of one tile. cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
+  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr) return true;
+  static EncodeTiledFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  p->tma_ok = false;
+  if (!encode) return false;
+  const int rank = p->rank;
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  dims[0] = 2ull * p->nf[0];
+  box[0] = 2u * (p->bin[0] + 8);
+  cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 8;
+  for (int d = 1; d < rank; ++d) {
+    dims[d] = p->nf[d];
+    box[d] = p->bin[d] + 8;
+    strides[d - 1] = row;
+    row *= p->nf[d];
+  }
+  dims[rank] = ntr;
+  box[rank] = 1;
+  strides[rank - 1] = static_cast<cuuint64_t>(p->nftot) * 8;
+  for (int d = 0; d <= rank; ++d) if (box[d] > 256) return false;
+  CUresult r = encode(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank + 1, const_cast<void*>(grid), dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  p->tmap_ptr = grid;
+  p->tmap_batch = ntr;
+  p->tma_ok = true;
+  return true;
+}
+
 template <int RANK>
-cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = interp_tile_smem_bytes<RANK, kInterpWarps>(p->bin);
 #define INTERP_CASE(NS)                                                                          \
@@ -232,7 +284,7 @@ cudaError_t launch_interp_tile(const b200nufft_plan* p, int ntr, const float2* f
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kInterpWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),    \
                                              p->idx, p->start.as<int4>(), p->wrec.as<float4>(),  \
-                                             fw, c);                                             \
+                                             fw, c, p->tmap, use_tma);                           \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
