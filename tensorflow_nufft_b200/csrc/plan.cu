@@ -501,10 +501,22 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   p->launches++;
 
   const int align_x = (!p->is_double) ? 1 : 0;
-  stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
-      M, rank, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns,
-      static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
-      p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
+  if (p->PX == 8 && p->PY == 8 && rank >= 2) {
+    const F beta = static_cast<F>(p->kp.beta), cc = static_cast<F>(p->kp.c), hw = static_cast<F>(p->kp.half_width);
+    if (rank == 2)
+      stencil_record8_kernel<F, 2><<<grid_for(M * 2, 256, 16), 256, 0, st>>>(
+          M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
+          align_x, p->start.as<int>(), p->wrec.as<F>());
+    else
+      stencil_record8_kernel<F, 3><<<grid_for(M * 3, 256, 16), 256, 0, st>>>(
+          M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
+          align_x, p->start.as<int>(), p->wrec.as<F>());
+  } else {
+    stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
+        M, rank, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns,
+        static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
+        p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
+  }
   LAUNCH_OK(p);
   p->launches++;
 

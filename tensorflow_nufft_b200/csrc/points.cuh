@@ -199,6 +199,43 @@ __device__ __forceinline__ F es_eval(F x, F beta, F c, F half_width) {
   return (fabs(x) >= half_width) ? F(0) : k;
 }
 
+// float specialisation of the exponent e = fl32(beta * sqrt(1 - t)) WITHOUT fp64 instructions:
+// 1 - t is held exactly as a float pair (Fast2Sum), the square root and the product with beta are
+// carried in float-float arithmetic (error ~2^-44), and the final sum rounds to the same float the
+// double evaluation gives (up to rare double-rounding ties). ~20 fp32 instructions instead of a
+// DSQRT expansion; near the stencil edge (1 - t tiny) it falls back to the double path.
+__device__ __forceinline__ float es_exponent_ff(float t, float beta) {
+  const float a_hi = __fsub_rn(1.0f, t);
+  if (!(a_hi > 1e-5f)) {
+    double a = 1.0 - static_cast<double>(t);
+    a = a < 0.0 ? 0.0 : a;
+    return static_cast<float>(static_cast<double>(beta) * sqrt(a));
+  }
+  const float a_lo = __fsub_rn(-t, __fsub_rn(a_hi, 1.0f));          // exact: (1 - t) = a_hi + a_lo
+  const float r0 = __fsqrt_rn(a_hi);
+  const float res = __fadd_rn(__fmaf_rn(-r0, r0, a_hi), a_lo);      // (a_hi + a_lo) - r0^2
+  const float r1 = __fmul_rn(res, __fdividef(0.5f, r0));            // sqrt = r0 + r1
+  const float p = __fmul_rn(beta, r0);
+  const float pe = __fmaf_rn(beta, r0, -p);                         // exact error of the product
+  return __fadd_rn(p, __fmaf_rn(beta, r1, pe));
+}
+
+template <typename F>
+__device__ __forceinline__ F es_eval_fast(F x, F beta, F c, F half_width) {
+  return es_eval<F>(x, beta, c, half_width);
+}
+template <>
+__device__ __forceinline__ float es_eval_fast<float>(float x, float beta, float c, float half_width) {
+  const float t = mul_rn(mul_rn(c, x), x);
+  const float e = es_exponent_ff(t, beta);
+#ifdef B200NUFFT_FAST_EXP
+  const float k = expf(e);
+#else
+  const float k = static_cast<float>(exp(static_cast<double>(e)));
+#endif
+  return (fabsf(x) >= half_width) ? 0.f : k;
+}
+
 // Per-point stencil record, in sorted order j (point id idx[j]):
 //   start[j] = {x0, i1y, i1z, shift}   x0 = i1x - shift, shift = (i1x & 1) if align_x else 0
 //   wrec[j][R] = { wx[PX], wy[PY] (rank>1), wz[PY] (rank>2) }
@@ -225,13 +262,49 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
     const F x1 = sub_rn(static_cast<F>(i1), x);
     const int shift = (d == 0 && align_x) ? (i1 & 1) : 0;
     const int t = tap - shift;
-    wrec[g] = (t >= 0 && t < ns) ? es_eval<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
+    F wv = F(0);
+    if (t >= 0 && t < ns) wv = es_eval_fast<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width);
+    wrec[g] = wv;
     if (k == 0) {
       int4 st = make_int4(i1 - shift, 0, 0, shift);
       if (rank > 1) st.y = static_cast<int>(ceil(sub_rn(f1[i], half_width)));
       if (rank > 2) st.z = static_cast<int>(ceil(sub_rn(f2[i], half_width)));
       start[j] = st;
     }
+  }
+}
+
+// Fast path of the record kernel for the tile kernels' layout (PX = PY = 8, ns <= 7):
+// one thread per (point, dimension) computes the stencil start once and its 8 weights, and stores
+// them as two 128-bit writes (adjacent threads write adjacent 32-byte chunks: fully coalesced).
+template <typename F, int RANK>
+__global__ void __launch_bounds__(256)
+stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restrict__ f0,
+                       const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
+                       int align_x, int* __restrict__ start /* int4 per point */, F* __restrict__ wrec) {
+  const int64_t total = M * RANK;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
+    const int64_t j = g / RANK;
+    const int d = static_cast<int>(g - j * RANK);
+    const int i = idx[j];
+    const F* fd = d == 0 ? f0 : (d == 1 ? f1 : f2);
+    const F x = fd[i];
+    const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
+    const F x1 = sub_rn(static_cast<F>(i1), x);
+    const int shift = (d == 0 && align_x) ? (i1 & 1) : 0;
+    F w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = k - shift;
+      w[k] = (t >= 0 && t < ns) ? es_eval_fast<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
+    }
+    F* out = wrec + g * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = w[k];
+    int* st = start + 4 * j;
+    if (d == 0) { st[0] = i1 - shift; st[3] = shift; if (RANK < 2) st[1] = 0; if (RANK < 3) st[2] = 0; }
+    else st[d] = i1;
   }
 }
 

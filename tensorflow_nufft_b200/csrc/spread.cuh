@@ -227,28 +227,27 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
           }
         } else {
           const int tz = __float_as_int(of_c.y);
-          // first stencil plane owned by this warp: (tz + dz) % WPT == warp
-          int dz0 = (warp - tz) % WPT;
-          dz0 = dz0 < 0 ? dz0 + WPT : dz0;
+          // first stencil plane owned by this warp: (tz + dz) % WPT == warp   (WPT is a power of two)
+          static_assert((WPT & (WPT - 1)) == 0, "WPT must be a power of two");
+          const int dz0 = (warp - tz) & (WPT - 1);
           if (row_ok && dz0 < NS) {
-            float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off);
+            float4* ptr = reinterpret_cast<float4*>(tile + off + lane_off) + dz0 * zstride4;
+            const float* wzp = rec + 28 + dz0;
             constexpr int KMAX = (NS + WPT - 1) / WPT;
             float4 v[KMAX];
             float w[KMAX];
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-              const int dz = dz0 + k * WPT;
-              if (dz < NS) {
-                v[k] = ptr[dz * zstride4];
-                w[k] = rec[28 + dz];
+              if (k == 0 || dz0 + k * WPT < NS) {
+                v[k] = ptr[k * WPT * zstride4];
+                w[k] = wzp[k * WPT];
               }
             }
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-              const int dz = dz0 + k * WPT;
-              if (dz < NS) {
+              if (k == 0 || dz0 + k * WPT < NS) {
                 v[k].x += w[k] * cx.x; v[k].y += w[k] * cx.y; v[k].z += w[k] * cx.z; v[k].w += w[k] * cx.w;
-                ptr[dz * zstride4] = v[k];
+                ptr[k * WPT * zstride4] = v[k];
               }
             }
           }
