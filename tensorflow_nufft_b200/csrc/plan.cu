@@ -484,11 +484,27 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
 
   p->launches += exclusive_scan_i32(p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->nbtot,
                                     p->scan_tmp(), nullptr, st);
-  subproblem_count_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub,
-                                                                  p->num_sub.as<int>());
-  p->launches++;
-  p->launches += exclusive_scan_i32(p->num_sub.as<int>(), p->sub_start.as<int>(), p->nbtot, p->scan_tmp(),
-                                    p->sub_total(), st);
+  // Points per subproblem: the reference caps at 1024 (gpu_max_subproblem_size, nufft_options.h:153).
+  // Small point sets get smaller subproblems so that the launch still fills the 148 SMs.
+  if (p->opts.max_subproblem_size > 0) {
+    p->msub = p->opts.max_subproblem_size;
+  } else {
+    const int64_t per_item = M * std::min(p->ntransf, p->batch) / (static_cast<int64_t>(kNumSMsB200) * 16);
+    int ms = 64;
+    while (ms < 1024 && ms < per_item) ms *= 2;
+    p->msub = ms;
+  }
+  if (p->nbtot <= kScanSmallMax) {
+    scan_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
+                                         p->sub_total());
+    p->launches++;
+  } else {
+    subproblem_count_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub,
+                                                                    p->num_sub.as<int>());
+    p->launches++;
+    p->launches += exclusive_scan_i32(p->num_sub.as<int>(), p->sub_start.as<int>(), p->nbtot, p->scan_tmp(),
+                                      p->sub_total(), st);
+  }
   LAUNCH_OK(p);
   // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
   // launch the bound, surplus CTAs exit on the device-side count.
@@ -588,7 +604,7 @@ int create_impl(b200nufft_plan* p) {
     p->nbins[d] = d < p->rank ? (p->nf[d] + p->bin[d] - 1) / p->bin[d] : 1;
     p->nbtot *= p->nbins[d];
   }
-  p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;
+  p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && p->spread_method == 3;
   if (p->ws && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)

@@ -103,12 +103,50 @@ scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int64_t n, 
   }
 }
 
+// Single-CTA scan for small arrays (bins of a 2D plan, radix histograms of small point sets): one
+// launch instead of three. Optional element transform: v -> ceil(v / div) when div > 0
+// (subproblem counts, CalcSubproblemKernel nufft_plan.cu.cc:304-310, fused into the scan).
+constexpr int kScanSmallMax = 32768;
+__global__ void __launch_bounds__(1024)
+scan_small_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int div, int* __restrict__ total_out) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    int v = i < n ? in[i] : 0;
+    if (div > 0) v = (v + div - 1) / div;
+    int incl = warp_incl_scan(v);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int s = wsum[lane];
+      int si = warp_incl_scan(s);
+      wsum[lane] = si - s;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + wsum[warp] + incl - v;
+    if (i < n) out[i] = excl;
+    __syncthreads();
+    if (t == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (t == 0 && total_out) *total_out = carry_s;
+}
+
 // tmp must hold kScanMaxBlocks ints. Returns the number of kernels launched.
 inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_out,
                               cudaStream_t stream) {
   if (n <= 0) {
     if (total_out) cudaMemsetAsync(total_out, 0, sizeof(int), stream);
     return 0;
+  }
+  if (n <= kScanSmallMax) {
+    scan_small_kernel<<<1, 1024, 0, stream>>>(in, out, static_cast<int>(n), 0, total_out);
+    return 1;
   }
   int nb = static_cast<int>(std::min<int64_t>(kScanMaxBlocks, (n + 4 * kScanTile - 1) / (4 * kScanTile)));
   int64_t chunk = (n + nb - 1) / nb;
