@@ -141,6 +141,10 @@ class Plan:
       if k == "bin_dims":
         for i, b in enumerate(v):
           opts.bin_dims[i] = int(b)
+      elif k == "no_tma":
+        opts.reserved[0] = int(v)
+      elif k == "coils_per_cta":
+        opts.reserved[1] = int(v)
       else:
         if not hasattr(opts, k):
           raise TypeError(f"unknown option {k}")

@@ -203,14 +203,14 @@ cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c
   return cudaGetLastError();
 }
 
-template <int RANK, int TZ>
+template <int RANK, int TZ, int NC>
 cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
-  const size_t smem = spread_ws_smem_bytes<RANK>(p->bin);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
+  const size_t smem = spread_ws_smem_bytes<RANK, NC>(p->bin);
 #define WS_CASE(NS)                                                                              \
   case NS: {                                                                                     \
-    auto k = spread_ws_f32_kernel<NS, RANK, TZ>;                                                 \
+    auto k = spread_ws_f32_kernel<NS, RANK, TZ, NC>;                                             \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
@@ -302,9 +302,16 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
     cudaError_t e;
     const float2* cc = static_cast<const float2*>(c);
     float2* ff = static_cast<float2*>(fw);
-    if (p->rank == 2) e = launch_spread_ws<2, 1>(p, ntr, cc, ff, st);
-    else if (p->bin[2] == 4) e = launch_spread_ws<3, 12>(p, ntr, cc, ff, st);
-    else if (p->bin[2] == 8) e = launch_spread_ws<3, 16>(p, ntr, cc, ff, st);
+    const int nc_opt = p->opts.reserved[1];   // coils per CTA override (0 = auto)
+    if (p->rank == 2) {
+      const int nc = nc_opt > 0 ? nc_opt : 4;
+      if (nc >= 8 && ntr % 8 == 0) e = launch_spread_ws<2, 1, 8>(p, ntr, cc, ff, st);
+      else if (nc >= 4 && ntr % 4 == 0) e = launch_spread_ws<2, 1, 4>(p, ntr, cc, ff, st);
+      else if (nc >= 2 && ntr % 2 == 0) e = launch_spread_ws<2, 1, 2>(p, ntr, cc, ff, st);
+      else e = launch_spread_ws<2, 1, 1>(p, ntr, cc, ff, st);
+    }
+    else if (p->bin[2] == 4) e = launch_spread_ws<3, 12, 1>(p, ntr, cc, ff, st);
+    else if (p->bin[2] == 8) e = launch_spread_ws<3, 16, 1>(p, ntr, cc, ff, st);
     else e = cudaErrorInvalidValue;
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread ws launch: %s", cudaGetErrorString(e));
   } else if (p->spread_method == 2) {
@@ -591,7 +598,12 @@ int create_impl(b200nufft_plan* p) {
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
   int def_bin[3] = {1, 1, 1};
   if (p->rank == 1) { def_bin[0] = 1024; }
-  else if (p->rank == 2) { def_bin[0] = 32; def_bin[1] = 32; }
+  else if (p->rank == 2) {
+    // window-sorted spreader: small tiles (24 x 16 cells) so that 4 coils' tiles + the stage fit
+    // ~8 CTAs per SM (measured best on cfg2: 0.48 ms per 8 coils vs 0.79 ms at 32 x 32)
+    def_bin[0] = (p->type == 1 && p->spread_method == 3) ? 16 : 32;
+    def_bin[1] = (p->type == 1 && p->spread_method == 3) ? 8 : 32;
+  }
   else {
     def_bin[0] = 16;
     def_bin[1] = 16;
@@ -618,7 +630,7 @@ int create_impl(b200nufft_plan* p) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
-    if (uses_tile && p->spread_method == 3) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2>(p->bin) : spread_ws_smem_bytes<3>(p->bin));
+    if (uses_tile && p->spread_method == 3) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
     if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;

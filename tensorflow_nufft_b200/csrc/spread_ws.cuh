@@ -18,17 +18,19 @@
 
 namespace b200 {
 
-template <int RANK> struct WsRec {
+template <int RANK, int NC> struct WsRec {
   // words: [0..7]   wx[8]
-  //        [8..23]  cw[r] = {Re c * wy[r], Im c * wy[r]}   r < 8
-  //        [24]     off2d (cells) of the stencil window, or -1 for a dropped point
-  //        [25]     tz (3D: tile z of the stencil start)
-  //        [26]     flag: 1 if this point opens a new run (window differs from the previous point)
-  //        [27]     pad
-  //        [28..35] wz[8]                                  (3D)
+  //        [8]      2 * off2d + flag; off2d = window offset in cells (-1: dropped point),
+  //                 flag = 1 if this point opens a new run (window differs from the previous point)
+  //        [9]      tz (3D: tile z of the stencil start)        [10..11] pad
+  //        [12 + 16 k ...] cw_k[r] = {Re c_k * wy[r], Im c_k * wy[r]}, r < 8, for each of the NC coils
+  //        [12 + 16 NC ...] wz[8]                                  (3D)
   // 128-bit shared loads always cost 4 wavefronts (one per quarter warp) even when lanes share
-  // addresses, so the per-point broadcast data is read with 64/32-bit loads (1 wavefront each).
-  static constexpr int kStride = RANK == 3 ? 44 : 36;   // = 12 / 4 mod 32 words: conflict-free staging
+  // addresses, so the per-point broadcast data is read with 64/32-bit loads.
+  static constexpr int kCw = 12;
+  static constexpr int kWz = 12 + 16 * NC;
+  static constexpr int kStride = kWz + (RANK == 3 ? 8 : 0);   // 4 * odd words: conflict-free staging
+  static_assert((kStride / 4) % 2 == 1, "stage stride must be an odd multiple of 4 words");
 };
 
 template <int NS, int TZ, int TZ0>
@@ -60,7 +62,10 @@ struct ColumnDispatch<NS, TZ, -1> {
 };
 
 // TZ = bin_z + 8 for RANK 3 (compile time: the z-column lives in registers), 1 for RANK 2.
-template <int NS, int RANK, int TZ>
+// NC = coils (transforms) handled by one CTA (2D only): the per-point work that does not depend on
+// the coil -- weight loads, run detection, loop control -- is shared by NC accumulator sets and NC
+// tiles, which cuts instructions and shared-memory traffic per point-transform by ~NC/2.
+template <int NS, int RANK, int TZ, int NC>
 __global__ void __launch_bounds__(32)
 spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
@@ -69,7 +74,9 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   constexpr int QX = (NS + 2) / 2;
   static_assert(QX * NS <= 32, "stencil slab must fit one warp");
   constexpr int C4 = 2 * RANK;
-  constexpr int SW = WsRec<RANK>::kStride;
+  static_assert(RANK == 2 || NC == 1, "multi-coil CTAs are 2D only");
+  using Rec = WsRec<RANK, NC>;
+  constexpr int SW = Rec::kStride;
   constexpr int BS = 32;
   extern __shared__ float4 smem4[];
 
@@ -87,11 +94,11 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
   const int plane = TX * TY;
   const int ncell = plane * TZ;
-  float4* tile4 = smem4;
+  float4* tile4 = smem4;                                        // [NC][ncell / 2]
   float2* tile = reinterpret_cast<float2*>(tile4);
-  float* stage = reinterpret_cast<float*>(smem4 + ncell / 2);   // [BS][SW]
+  float* stage = reinterpret_cast<float*>(smem4 + NC * (ncell / 2));   // [BS + 1][SW]
 
-  for (int i = lane; i < ncell / 2; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < NC * (ncell / 2); i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int q = lane % QX;
   const int r = lane / QX;
@@ -100,13 +107,15 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   const int lane_off = rr * TX + 2 * q;
   const int zstride4 = plane / 2;
 
-  const float2* ct = c + static_cast<int64_t>(t) * M;
-  float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+  const float2* ct = c + static_cast<int64_t>(t) * NC * M;      // coil k: ct + k * M
+  float2* fwt = fw + static_cast<int64_t>(t) * NC * g.nftot;
 
   // ---- register prefetch of this lane's point of the next batch ----
   float4 w4[C4];
   int4 st_n = make_int4(0, 0, 0, 0);
-  float2 c_n = make_float2(0.f, 0.f);
+  float2 c_n[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) c_n[k] = make_float2(0.f, 0.f);
   int id_n2 = 0;
   auto fetch = [&](int bb) {
     const int pl = bb * BS + lane;
@@ -115,7 +124,8 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
 #pragma unroll
       for (int k = 0; k < C4; ++k) w4[k] = wrec4[j * C4 + k];
       st_n = start[j];
-      c_n = ct[id_n2];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) c_n[k] = ct[static_cast<int64_t>(k) * M + id_n2];
     }
     const int pl2 = (bb + 1) * BS + lane;
     if (pl2 < np) id_n2 = idx[p0 + pl2];
@@ -140,37 +150,44 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     last_off = __shfl_sync(0xffffffffu, off, 31);
     rec4[0] = w4[0];
     rec4[1] = w4[1];
-    const float cre = c_n.x, cim = c_n.y;
-    rec4[2] = make_float4(cre * w4[2].x, cim * w4[2].x, cre * w4[2].y, cim * w4[2].y);
-    rec4[3] = make_float4(cre * w4[2].z, cim * w4[2].z, cre * w4[2].w, cim * w4[2].w);
-    rec4[4] = make_float4(cre * w4[3].x, cim * w4[3].x, cre * w4[3].y, cim * w4[3].y);
-    rec4[5] = make_float4(cre * w4[3].z, cim * w4[3].z, cre * w4[3].w, cim * w4[3].w);
-    rec4[6] = make_float4(__int_as_float(off), __int_as_float(tz), __int_as_float(flag), 0.f);
-    if (RANK > 2) { rec4[7] = w4[C4 - 2]; rec4[8] = w4[C4 - 1]; }
+    rec4[2] = make_float4(__int_as_float(off * 2 + flag), __int_as_float(tz), 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const float cre = c_n[k].x, cim = c_n[k].y;
+      rec4[3 + 4 * k] = make_float4(cre * w4[2].x, cim * w4[2].x, cre * w4[2].y, cim * w4[2].y);
+      rec4[4 + 4 * k] = make_float4(cre * w4[2].z, cim * w4[2].z, cre * w4[2].w, cim * w4[2].w);
+      rec4[5 + 4 * k] = make_float4(cre * w4[3].x, cim * w4[3].x, cre * w4[3].y, cim * w4[3].y);
+      rec4[6 + 4 * k] = make_float4(cre * w4[3].z, cim * w4[3].z, cre * w4[3].w, cim * w4[3].w);
+    }
+    if (RANK > 2) { rec4[3 + 4 * NC] = w4[C4 - 2]; rec4[4 + 4 * NC] = w4[C4 - 1]; }
   };
   if (lane < np) id_n2 = idx[p0 + lane];
   fetch(0);
 
-  // ---- run accumulator ----
-  float4 v[TZ];
+  // ---- run accumulators: v[coil][plane] ----
+  constexpr int NV = NC * TZ;
+  float4 v[NV];
 #pragma unroll
-  for (int z = 0; z < TZ; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < NV; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cur = -1;   // 2D window offset (cells) of the open run, -1 = none
   int zlo = TZ, zhi = 0;   // planes touched by the open run (warp-uniform)
   auto flush_run = [&]() {
     if (cur >= 0 && row_ok) {
-      float4* ptr = reinterpret_cast<float4*>(tile + cur + lane_off);
 #pragma unroll
-      for (int z = 0; z < TZ; ++z) {
-        if (RANK == 2 || (z >= zlo && z < zhi)) {
-          float4 tv = ptr[z * zstride4];
-          tv.x += v[z].x; tv.y += v[z].y; tv.z += v[z].z; tv.w += v[z].w;
-          ptr[z * zstride4] = tv;
+      for (int k = 0; k < NC; ++k) {
+        float4* ptr = reinterpret_cast<float4*>(tile + static_cast<size_t>(k) * ncell + cur + lane_off);
+#pragma unroll
+        for (int z = 0; z < TZ; ++z) {
+          if (RANK == 2 || (z >= zlo && z < zhi)) {
+            float4 tv = ptr[z * zstride4];
+            tv.x += v[k * TZ + z].x; tv.y += v[k * TZ + z].y; tv.z += v[k * TZ + z].z; tv.w += v[k * TZ + z].w;
+            ptr[z * zstride4] = tv;
+          }
         }
       }
     }
 #pragma unroll
-    for (int z = 0; z < TZ; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < NV; ++z) v[z] = make_float4(0.f, 0.f, 0.f, 0.f);
     zlo = TZ;
     zhi = 0;
     __syncwarp();
@@ -185,35 +202,43 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     const int cnt = min(BS, np - bb * BS);
     // The stage holds BS + 1 records so that the prefetch of point p + 1 never needs a guard.
     float2 wx = *reinterpret_cast<const float2*>(stage + 2 * q);
-    float2 cw = *reinterpret_cast<const float2*>(stage + 8 + 2 * rr);
-    float2 of = *reinterpret_cast<const float2*>(stage + 24);
-    int fl = __float_as_int(stage[26]);
+    int of = __float_as_int(stage[8]);
+    float2 cw[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) cw[k] = *reinterpret_cast<const float2*>(stage + Rec::kCw + 16 * k + 2 * rr);
 #pragma unroll 2
     for (int p = 0; p < cnt; ++p) {
       const float* rec = stage + p * SW;
-      const float2 wx_c = wx, cw_c = cw, of_c = of;
-      const int fl_c = fl;
+      const float2 wx_c = wx;
+      const int of_c = of;
+      float2 cw_c[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) cw_c[k] = cw[k];
       wx = *reinterpret_cast<const float2*>(rec + SW + 2 * q);
-      cw = *reinterpret_cast<const float2*>(rec + SW + 8 + 2 * rr);
-      of = *reinterpret_cast<const float2*>(rec + SW + 24);
-      fl = __float_as_int(rec[SW + 26]);
-      if (fl_c) {              // warp-uniform
+      of = __float_as_int(rec[SW + 8]);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) cw[k] = *reinterpret_cast<const float2*>(rec + SW + Rec::kCw + 16 * k + 2 * rr);
+      if (of_c & 1) {          // warp-uniform: this point opens a new run
         flush_run();
-        cur = __float_as_int(of_c.x);
+        cur = of_c >> 1;
       }
       // dropped points carry cur = -1 and are accumulated into registers that are never stored
-      const float4 cx = make_float4(cw_c.x * wx_c.x, cw_c.y * wx_c.x, cw_c.x * wx_c.y, cw_c.y * wx_c.y);
       if constexpr (RANK == 2) {
-        v[0].x += cx.x; v[0].y += cx.y; v[0].z += cx.z; v[0].w += cx.w;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          v[k].x += cw_c[k].x * wx_c.x; v[k].y += cw_c[k].y * wx_c.x;
+          v[k].z += cw_c[k].x * wx_c.y; v[k].w += cw_c[k].y * wx_c.y;
+        }
       } else {
+        const float4 cx = make_float4(cw_c[0].x * wx_c.x, cw_c[0].y * wx_c.x, cw_c[0].x * wx_c.y, cw_c[0].y * wx_c.y);
         float wz[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 t2 = *reinterpret_cast<const float2*>(rec + 28 + 2 * k);
+          const float2 t2 = *reinterpret_cast<const float2*>(rec + Rec::kWz + 2 * k);
           wz[2 * k] = t2.x;
           wz[2 * k + 1] = t2.y;
         }
-        const int tz = __float_as_int(of_c.y);
+        const int tz = __float_as_int(rec[9]);
         zlo = min(zlo, tz);
         zhi = max(zhi, tz + NS);
         ColumnDispatch<NS, TZ, TZ - NS>::run(tz, v, wz, cx);
@@ -223,26 +248,29 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   }
   flush_run();
 
-  // Flush the tile: two complex cells per REDG.ADD.F32x4; periodic wrap; zero pairs skipped.
+  // Flush the tiles: two complex cells per REDG.ADD.F32x4; periodic wrap; zero pairs skipped.
   const int TXH = TX / 2;
   for (int i = lane; i < ncell / 2; i += 32) {
-    const float4 tv = tile4[i];
-    if (tv.x == 0.f && tv.y == 0.f && tv.z == 0.f && tv.w == 0.f) continue;
     const int ix = i % TXH;
     const int iy = (i / TXH) % TY;
     const int iz = i / (TXH * TY);
     const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
     const int gy = mod_idx(oy + iy, g.nf[1]);
     const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
-    float2* dst = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
-    red_add(reinterpret_cast<float4*>(dst), tv);
+    const int64_t cell = (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const float4 tv = tile4[k * (ncell / 2) + i];
+      if (tv.x == 0.f && tv.y == 0.f && tv.z == 0.f && tv.w == 0.f) continue;
+      red_add(reinterpret_cast<float4*>(fwt + static_cast<int64_t>(k) * g.nftot + cell), tv);
+    }
   }
 }
 
-template <int RANK>
+template <int RANK, int NC>
 inline size_t spread_ws_smem_bytes(const int* bin) {
   const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
-  return ncell * sizeof(float2) + 33 * WsRec<RANK>::kStride * sizeof(float);
+  return NC * ncell * sizeof(float2) + 33 * WsRec<RANK, NC>::kStride * sizeof(float);
 }
 
 }  // namespace b200
