@@ -14,7 +14,7 @@ def run(name, ttype, grid, pts, T, methods, reps=5, bin_dims=None, msub=0):
   c = torch.from_numpy(H.random_complex((T, M), 1)).cuda()
   f = torch.from_numpy(H.random_complex((T, N), 2)).cuda()
   for meth in methods:
-    kw = dict(spread_method=meth, interp_method=meth, profile=1, max_subproblem_size=msub)
+    kw = dict(spread_method=min(meth, 3) if ttype == 1 else 0, interp_method=meth if ttype == 2 else 0, profile=1, max_subproblem_size=msub)
     if bin_dims: kw["bin_dims"] = bin_dims
     plan = _lib.Plan(ttype, grid[::-1], -1, T, 1e-6, 0, device=0, **kw)
     st = torch.cuda.current_stream().cuda_stream
@@ -40,12 +40,12 @@ def run(name, ttype, grid, pts, T, methods, reps=5, bin_dims=None, msub=0):
 if __name__ == "__main__":
   which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
   if "cfg1" in which:
-    run("cfg1-radial-256", 2, (256, 256), H.radial_points(200, 500), 1, (1, 2))
+    run("cfg1-radial-256", 2, (256, 256), H.radial_points(200, 500), 1, (1, 2, 3))
     run("cfg1-radial-256-t1", 1, (256, 256), H.radial_points(200, 500), 1, (1, 2, 3))
   if "cfg2" in which:
     p = H.spiral_points(32, 62500)
     run("cfg2-spiral-512-T8", 1, (512, 512), p, 8, (2, 3))
-    run("cfg2-spiral-512-T8-type2", 2, (512, 512), p, 8, (1, 2))
+    run("cfg2-spiral-512-T8-type2", 2, (512, 512), p, 8, (2, 3))
   if "cfg3" in which:
     p = H.uniform_points(8000000, 3, 3)
     run("cfg3-uniform-128", 1, (128, 128, 128), p, 1, (2,), bin_dims=(16, 16, 2))
@@ -53,10 +53,11 @@ if __name__ == "__main__":
     run("cfg3-uniform-128-ws-16x16x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(16, 16, 8))
     run("cfg3-uniform-128-ws-16x8x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(16, 8, 8))
     run("cfg3-uniform-128-ws-32x8x8", 1, (128, 128, 128), p, 1, (3,), bin_dims=(32, 8, 8))
-    run("cfg3-uniform-128-type2", 2, (128, 128, 128), p, 1, (1, 2))
+    run("cfg3-uniform-128-type2", 2, (128, 128, 128), p, 1, (2, 3))
     run("cfg3-uniform-128-type2-bin2", 2, (128, 128, 128), p, 1, (2,), bin_dims=(16, 16, 2))
   if "cfg4" in which:
     p = H.stack_of_stars_points(125, 125, 256)
-    run("cfg4-sos-256-T2", 2, (256, 256, 256), p, 2, (1, 2))
+    run("cfg4-sos-256-T2", 2, (256, 256, 256), p, 2, (2, 3))
+    run("cfg4-sos-256-T2-bin8", 2, (256, 256, 256), p, 2, (3,), bin_dims=(16, 16, 8))
     run("cfg4-sos-256-T2-type1", 1, (256, 256, 256), p, 2, (2,), bin_dims=(16, 16, 2))
     run("cfg4-sos-256-T2-type1-ws", 1, (256, 256, 256), p, 2, (3,))

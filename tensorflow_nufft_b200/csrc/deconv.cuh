@@ -16,86 +16,96 @@ struct ModeGeom {
   int64_t ntot, nftot;
 };
 
-// grid: (ceil(N/256), ntr). fk[t][N] = fw[t][wrap(k)] / factor
+// Row-based mapping: one CTA per (row of the fastest axis, transform). The slow-axis indices and the
+// slow-axis prefactor (1/p3)/p2 are computed once per row, no per-element integer division; x is
+// walked with coalesced accesses.
+// grid: (n2*n3, ntr). fk[t][i3][i2][i1] = fw[t][wrap(k)] / factor
 template <typename F>
 __global__ void __launch_bounds__(256)
 deconvolve_kernel(ModeGeom m, const F* __restrict__ p1, const F* __restrict__ p2, const F* __restrict__ p3,
                   const Cplx<F>* __restrict__ fw, Cplx<F>* __restrict__ fk) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= m.ntot) return;
+  const int row = blockIdx.x;
   const int t = blockIdx.y;
-  const int i1 = static_cast<int>(i % m.n[0]);
-  const int64_t r = i / m.n[0];
-  const int i2 = m.rank > 1 ? static_cast<int>(r % m.n[1]) : 0;
-  const int i3 = m.rank > 2 ? static_cast<int>(r / m.n[1]) : 0;
-  const int k1 = i1 - m.n[0] / 2;
-  const int w1 = k1 >= 0 ? k1 : m.nf[0] + k1;
+  const int i2 = m.rank > 1 ? row % m.n[1] : 0;
+  const int i3 = m.rank > 2 ? row / m.n[1] : 0;
   F pre = F(1);
-  int64_t in = w1;
+  int64_t in_row = 0;
   if (m.rank > 2) {
     const int k3 = i3 - m.n[2] / 2;
     const int w3 = k3 >= 0 ? k3 : m.nf[2] + k3;
     pre = pre / p3[abs(k3)];
-    in += static_cast<int64_t>(w3) * m.nf[0] * m.nf[1];
+    in_row += static_cast<int64_t>(w3) * m.nf[0] * m.nf[1];
   }
   if (m.rank > 1) {
     const int k2 = i2 - m.n[1] / 2;
     const int w2 = k2 >= 0 ? k2 : m.nf[1] + k2;
     pre = pre / p2[abs(k2)];
-    in += static_cast<int64_t>(w2) * m.nf[0];
+    in_row += static_cast<int64_t>(w2) * m.nf[0];
   }
-  const F f1 = p1[abs(k1)];
-  const Cplx<F> v = fw[static_cast<int64_t>(t) * m.nftot + in];
-  fk[static_cast<int64_t>(t) * m.ntot + i] = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+  const Cplx<F>* src = fw + static_cast<int64_t>(t) * m.nftot + in_row;
+  Cplx<F>* dst = fk + static_cast<int64_t>(t) * m.ntot + static_cast<int64_t>(row) * m.n[0];
+  const int half = m.n[0] / 2;
+  for (int i1 = threadIdx.x; i1 < m.n[0]; i1 += blockDim.x) {
+    const int k1 = i1 - half;
+    const int w1 = k1 >= 0 ? k1 : m.nf[0] + k1;
+    const F f1 = p1[abs(k1)];
+    const Cplx<F> v = src[w1];
+    dst[i1] = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+  }
 }
 
-// grid: (ceil(nftot/256), ntr). Writes EVERY fine cell: amplified mode or zero (no memset pass).
+// grid: (nf2*nf3, ntr). Writes EVERY fine cell of the row: amplified mode or zero (no memset pass).
 template <typename F>
 __global__ void __launch_bounds__(256)
 amplify_kernel(ModeGeom m, const F* __restrict__ p1, const F* __restrict__ p2, const F* __restrict__ p3,
                const Cplx<F>* __restrict__ fk, Cplx<F>* __restrict__ fw) {
-  const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (w >= m.nftot) return;
+  const int row = blockIdx.x;
   const int t = blockIdx.y;
-  const int w1 = static_cast<int>(w % m.nf[0]);
-  const int64_t r = w / m.nf[0];
-  const int w2 = m.rank > 1 ? static_cast<int>(r % m.nf[1]) : 0;
-  const int w3 = m.rank > 2 ? static_cast<int>(r / m.nf[1]) : 0;
+  const int w2 = m.rank > 1 ? row % m.nf[1] : 0;
+  const int w3 = m.rank > 2 ? row / m.nf[1] : 0;
   // mode k_d present iff w_d <= kmax_d (k = w) or w_d >= nf_d + kmin_d (k = w - nf)
   bool ok = true;
-  int k1, k2 = 0, k3 = 0;
-  {
-    const int kmax = (m.n[0] - 1) / 2, kmin = -(m.n[0] / 2);
-    k1 = w1 <= kmax ? w1 : w1 - m.nf[0];
-    ok = ok && (w1 <= kmax || w1 >= m.nf[0] + kmin);
+  F pre = F(1);
+  int64_t src_row = 0;
+  if (m.rank > 2) {
+    const int kmax = (m.n[2] - 1) / 2, kmin = -(m.n[2] / 2);
+    const int k3 = w3 <= kmax ? w3 : w3 - m.nf[2];
+    ok = ok && (w3 <= kmax || w3 >= m.nf[2] + kmin);
+    if (ok) {
+      pre = pre / p3[abs(k3)];
+      src_row += static_cast<int64_t>(k3 + m.n[2] / 2) * m.n[0] * m.n[1];
+    }
   }
   if (m.rank > 1) {
     const int kmax = (m.n[1] - 1) / 2, kmin = -(m.n[1] / 2);
-    k2 = w2 <= kmax ? w2 : w2 - m.nf[1];
-    ok = ok && (w2 <= kmax || w2 >= m.nf[1] + kmin);
-  }
-  if (m.rank > 2) {
-    const int kmax = (m.n[2] - 1) / 2, kmin = -(m.n[2] / 2);
-    k3 = w3 <= kmax ? w3 : w3 - m.nf[2];
-    ok = ok && (w3 <= kmax || w3 >= m.nf[2] + kmin);
-  }
-  Cplx<F> out = make_cplx<F>(F(0), F(0));
-  if (ok) {
-    F pre = F(1);
-    int64_t i = k1 + m.n[0] / 2;
-    if (m.rank > 2) {
-      pre = pre / p3[abs(k3)];
-      i += static_cast<int64_t>(k3 + m.n[2] / 2) * m.n[0] * m.n[1];
-    }
-    if (m.rank > 1) {
+    const int k2 = w2 <= kmax ? w2 : w2 - m.nf[1];
+    const bool ok2 = (w2 <= kmax || w2 >= m.nf[1] + kmin);
+    if (ok && ok2) {
       pre = pre / p2[abs(k2)];
-      i += static_cast<int64_t>(k2 + m.n[1] / 2) * m.n[0];
+      src_row += static_cast<int64_t>(k2 + m.n[1] / 2) * m.n[0];
     }
-    const F f1 = p1[abs(k1)];
-    const Cplx<F> v = fk[static_cast<int64_t>(t) * m.ntot + i];
-    out = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+    ok = ok && ok2;
   }
-  fw[static_cast<int64_t>(t) * m.nftot + w] = out;
+  Cplx<F>* dst = fw + static_cast<int64_t>(t) * m.nftot + static_cast<int64_t>(row) * m.nf[0];
+  const Cplx<F> zero = make_cplx<F>(F(0), F(0));
+  if (!ok) {
+    for (int w1 = threadIdx.x; w1 < m.nf[0]; w1 += blockDim.x) dst[w1] = zero;
+    return;
+  }
+  const Cplx<F>* src = fk + static_cast<int64_t>(t) * m.ntot + src_row;
+  const int kmax = (m.n[0] - 1) / 2, kmin = -(m.n[0] / 2);
+  const int half = m.n[0] / 2;
+  for (int w1 = threadIdx.x; w1 < m.nf[0]; w1 += blockDim.x) {
+    Cplx<F> out = zero;
+    const bool in = (w1 <= kmax || w1 >= m.nf[0] + kmin);
+    if (in) {
+      const int k1 = w1 <= kmax ? w1 : w1 - m.nf[0];
+      const F f1 = p1[abs(k1)];
+      const Cplx<F> v = src[k1 + half];
+      out = make_cplx<F>((pre * v.x) / f1, (pre * v.y) / f1);
+    }
+    dst[w1] = out;
+  }
 }
 
 template <typename F>

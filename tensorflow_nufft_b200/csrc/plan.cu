@@ -295,6 +295,34 @@ cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, flo
   return cudaGetLastError();
 }
 
+constexpr int kPipeWarps = 2;
+
+template <int RANK>
+cudaError_t launch_interp_pipe(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
+  const size_t smem = interp_pipe_smem_bytes<RANK, kPipeWarps>(p->bin);
+  const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
+  const int64_t want = static_cast<int64_t>(p->sub_bound) * ntr;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(kNumSMsB200) * per_sm)));
+#define PIPE_CASE(NS)                                                                            \
+  case NS: {                                                                                     \
+    auto k = interp_pipe_f32_kernel<NS, RANK, kPipeWarps>;                                       \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, kPipeWarps * 32, smem, st>>>(p->M, g, ntr, p->sub_total(), p->sub_desc.as<int4>(), \
+                                           p->idx, p->start.as<int4>(), p->wrec.as<float4>(),    \
+                                           fw, c, p->tmap, use_tma);                             \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    PIPE_CASE(2) PIPE_CASE(3) PIPE_CASE(4) PIPE_CASE(5) PIPE_CASE(6) PIPE_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PIPE_CASE
+  return cudaGetLastError();
+}
+
 template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
@@ -333,7 +361,12 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
 template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->interp_method == 2) {
+  if (p->interp_method == 3) {
+    cudaError_t e = p->rank == 2
+        ? launch_interp_pipe<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
+        : launch_interp_pipe<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp pipe launch: %s", cudaGetErrorString(e));
+  } else if (p->interp_method == 2) {
     cudaError_t e = p->rank == 2
         ? launch_interp_tile<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
         : launch_interp_tile<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
@@ -409,15 +442,15 @@ int execute_impl(b200nufft_plan* p, void* c_, void* f_, cudaStream_t st) {
       rc = do_fft(p, ntr, st);
       if (rc) return rc;
       if (prof) cudaEventRecord(ev[2], st);
-      dim3 grid(ceil_div(p->n_modes_tot, 256), ntr);
-      deconvolve_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fw, fb);
+      dim3 grid(static_cast<unsigned>(p->n_modes_tot / p->n_modes[0]), ntr);
+      deconvolve_kernel<F><<<grid, std::min<int>(256, std::max<int>(32, ((int)p->n_modes[0] + 31) / 32 * 32)), 0, st>>>(mg, p1, p2, p3, fw, fb);
       LAUNCH_OK(p);
       p->launches++;
       if (prof) cudaEventRecord(ev[3], st);
     } else {
       if (prof) cudaEventRecord(ev[0], st);
-      dim3 grid(ceil_div(p->nftot, 256), ntr);
-      amplify_kernel<F><<<grid, 256, 0, st>>>(mg, p1, p2, p3, fb, fw);
+      dim3 grid(static_cast<unsigned>(p->nftot / p->nf[0]), ntr);
+      amplify_kernel<F><<<grid, std::min<int>(256, std::max<int>(32, (p->nf[0] + 31) / 32 * 32)), 0, st>>>(mg, p1, p2, p3, fb, fw);
       LAUNCH_OK(p);
       p->launches++;
       if (prof) cudaEventRecord(ev[1], st);
@@ -625,14 +658,15 @@ int create_impl(b200nufft_plan* p) {
     p->ws = false;
     p->spread_method = 2;
   }
-  const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method == 2 : false;
+  const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
   if (uses_tile || uses_tile_i) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
     if (uses_tile && p->spread_method == 3) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
-    if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
+    if (uses_tile_i && p->interp_method == 3) need = std::max(need, p->rank == 2 ? interp_pipe_smem_bytes<2, kPipeWarps>(p->bin) : interp_pipe_smem_bytes<3, kPipeWarps>(p->bin));
+    else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)
       return set_err(p, B200NUFFT_RESOURCE_EXHAUSTED, "tile of %zu bytes exceeds shared memory", p->tile_smem);

@@ -253,6 +253,33 @@ def test_full_size_adjointness_and_linearity(name):
   assert float(resid) < 5e-6
 
 
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4_half"])
+def test_full_size_parity_against_reference_cpu_plan(name):
+  """BASELINE configs at their full point counts and grids (fewer coils), engine vs the compiled
+  reference CPU plan driven with the GPU plan's parameters: rel-L2 <= max(2 tol, 1e-6) = 2e-6."""
+  tfft = _tfft()
+  from oracle import ref
+  if not ref.available():
+    pytest.skip("oracle/_ref/libref.so not present")
+  nthr = os.cpu_count() or 1
+  if name == "cfg2":
+    grid, pts, T, tt, direction = (512, 512), H.spiral_points(32, 62500), 2, 1, "backward"
+  elif name == "cfg3":
+    grid, pts, T, tt, direction = (128, 128, 128), H.uniform_points(8000000, 3, 3), 1, 1, "forward"
+  else:  # cfg4 at half the grid size per dim (the 512^3 fine grid is too slow for the CPU oracle's FFT)
+    grid, pts, T, tt, direction = (128, 128, 128), H.stack_of_stars_points(125, 125, 256), 2, 2, "forward"
+  M = pts.shape[0]
+  src = H.random_complex((T, M) if tt == 1 else (T,) + grid, 51)
+  out = tfft.nufft(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid_shape=grid,
+                   transform_type=f"type_{tt}", fft_direction=direction, tol=1e-6).cpu().numpy()
+  rp = ref.RefPlan(tt, list(grid[::-1]), -1 if direction == "forward" else 1, T, 1e-6, np.complex64,
+                   mode="gpuparams", num_threads=nthr)
+  rp.set_points(np.ascontiguousarray(pts[:, ::-1].T))
+  want = rp.execute(src.reshape(T, -1))
+  err = H.rel_l2(out.reshape(T, -1), want)
+  assert err <= 2e-6, f"{name}: rel L2 {err:.3e}"
+
+
 def test_full_size_cfg1_against_reference_and_sort_properties():
   """BASELINE config 1 (256^2, 100k radial points) against the compiled reference; plus bin-sort
   invariants read back through the parity hook: permutation, sortedness by bin, offsets = scan."""
