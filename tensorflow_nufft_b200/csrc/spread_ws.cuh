@@ -23,13 +23,18 @@ template <int RANK, int NC> struct WsRec {
   //        [8]      2 * off2d + flag; off2d = window offset in cells (-1: dropped point),
   //                 flag = 1 if this point opens a new run (window differs from the previous point)
   //        [9]      tz (3D: tile z of the stencil start)        [10..11] pad
-  //        [12 + 16 k ...] cw_k[r] = {Re c_k * wy[r], Im c_k * wy[r]}, r < 8, for each of the NC coils
-  //        [12 + 16 NC ...] wz[8]                                  (3D)
+  //        [12..19] wy[8]
+  //        [20 + 2 k]  c_k = strength of this point in coil k (re, im), k < NC
+  //        [kWz ...]   wz[8]                                       (3D)
+  // (c_k * wy[r] is formed on the fly: 2 FMUL per coil per point, in exchange for a stage record of
+  //  ~30 words instead of 12 + 16 NC, i.e. more resident CTAs per SM.)
   // 128-bit shared loads always cost 4 wavefronts (one per quarter warp) even when lanes share
   // addresses, so the per-point broadcast data is read with 64/32-bit loads.
-  static constexpr int kCw = 12;
-  static constexpr int kWz = 12 + 16 * NC;
-  static constexpr int kStride = kWz + (RANK == 3 ? 8 : 0);   // 4 * odd words: conflict-free staging
+  static constexpr int kWy = 12;
+  static constexpr int kC = 20;
+  static constexpr int kWz = 20 + ((2 * NC + 3) / 4) * 4;
+  static constexpr int kRaw = kWz + (RANK == 3 ? 8 : 0);
+  static constexpr int kStride = ((kRaw / 4) % 2 == 1) ? kRaw : kRaw + 4;   // 4 * odd words: conflict-free staging
   static_assert((kStride / 4) % 2 == 1, "stage stride must be an odd multiple of 4 words");
 };
 
@@ -152,15 +157,15 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     rec4[0] = w4[0];
     rec4[1] = w4[1];
     rec4[2] = make_float4(__int_as_float(off * 2 + flag), __int_as_float(tz), 0.f, 0.f);
+    rec4[3] = w4[2];
+    rec4[4] = w4[3];
+    float* recf = reinterpret_cast<float*>(rec4);
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const float cre = c_n[k].x, cim = c_n[k].y;
-      rec4[3 + 4 * k] = make_float4(cre * w4[2].x, cim * w4[2].x, cre * w4[2].y, cim * w4[2].y);
-      rec4[4 + 4 * k] = make_float4(cre * w4[2].z, cim * w4[2].z, cre * w4[2].w, cim * w4[2].w);
-      rec4[5 + 4 * k] = make_float4(cre * w4[3].x, cim * w4[3].x, cre * w4[3].y, cim * w4[3].y);
-      rec4[6 + 4 * k] = make_float4(cre * w4[3].z, cim * w4[3].z, cre * w4[3].w, cim * w4[3].w);
+    for (int k = 0; k < NC; ++k) *reinterpret_cast<float2*>(recf + Rec::kC + 2 * k) = c_n[k];
+    if (RANK > 2) {
+      *reinterpret_cast<float4*>(recf + Rec::kWz) = w4[C4 - 2];
+      *reinterpret_cast<float4*>(recf + Rec::kWz + 4) = w4[C4 - 1];
     }
-    if (RANK > 2) { rec4[3 + 4 * NC] = w4[C4 - 2]; rec4[4 + 4 * NC] = w4[C4 - 1]; }
   };
   if (lane < BS && lane < np) id_n2 = idx[p0 + lane];
   fetch(0);
@@ -204,9 +209,10 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     // The stage holds BS + 1 records so that the prefetch of point p + 1 never needs a guard.
     float2 wx = *reinterpret_cast<const float2*>(stage + 2 * q);
     int of = __float_as_int(stage[8]);
-    float2 cw[NC];
+    float wy = stage[Rec::kWy + rr];
+    float2 cc[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) cw[k] = *reinterpret_cast<const float2*>(stage + Rec::kCw + 16 * k + 2 * rr);
+    for (int k = 0; k < NC; ++k) cc[k] = *reinterpret_cast<const float2*>(stage + Rec::kC + 2 * k);
 #pragma unroll 2
     for (int p = 0; p < cnt; ++p) {
       const float* rec = stage + p * SW;
@@ -214,11 +220,12 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
       const int of_c = of;
       float2 cw_c[NC];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) cw_c[k] = cw[k];
+      for (int k = 0; k < NC; ++k) cw_c[k] = make_float2(cc[k].x * wy, cc[k].y * wy);
       wx = *reinterpret_cast<const float2*>(rec + SW + 2 * q);
       of = __float_as_int(rec[SW + 8]);
+      wy = rec[SW + Rec::kWy + rr];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) cw[k] = *reinterpret_cast<const float2*>(rec + SW + Rec::kCw + 16 * k + 2 * rr);
+      for (int k = 0; k < NC; ++k) cc[k] = *reinterpret_cast<const float2*>(rec + SW + Rec::kC + 2 * k);
       if (of_c & 1) {          // warp-uniform: this point opens a new run
         flush_run();
         cur = of_c >> 1;
