@@ -611,10 +611,10 @@ int create_impl(b200nufft_plan* p) {
   }
   // The reference batches min(T, 8) transforms (cuFINUFFT heuristic, nufft_plan.cu.cc:1923-1928).
   // With 180 GB of HBM a larger batch costs nothing and saves launches / tail effects (cfg2:
-  // 2.52 -> 2.39 ms per 32 coils): min(T, 32), capped so that the fine-grid batch stays <= 16 GiB.
+  // 2.52 -> 2.39 ms per 32 coils): min(T, 32), capped so that the fine-grid batch stays <= 4 GiB.
   {
     const int64_t grid_bytes = p->nftot * static_cast<int64_t>(sizeof(Cplx<F>));
-    const int cap = static_cast<int>(std::max<int64_t>(1, (int64_t(16) << 30) / std::max<int64_t>(1, grid_bytes)));
+    const int cap = static_cast<int>(std::max<int64_t>(1, (int64_t(4) << 30) / std::max<int64_t>(1, grid_bytes)));
     p->batch = p->opts.max_batch_size > 0 ? std::min(p->opts.max_batch_size, p->ntransf)
                                           : std::min(std::min(p->ntransf, 32), cap);
   }

@@ -156,6 +156,15 @@ CASES = [
     (3, (16, 20, 24), 5000, 1, 2, np.complex128, 1e-9, "uniform"),
     (3, (16, 20, 24), 5000, 1, 1, np.complex128, 1e-9, "uniform"),
     (2, (64, 64), 20000, 1, 1, np.complex64, 1e-7, "uniform"),   # ns = 8: generic kernels
+    # fine grids that are not multiples of the bin size (partial last bins, wrap inside a tile)
+    (2, (135, 77), 30000, 3, 1, np.complex64, 1e-6, "uniform"),
+    (2, (135, 77), 30000, 3, 2, np.complex64, 1e-6, "uniform"),
+    (3, (25, 27, 15), 20000, 2, 1, np.complex64, 1e-6, "uniform"),
+    (3, (25, 27, 15), 20000, 2, 2, np.complex64, 1e-6, "uniform"),
+    (2, (9, 7), 500, 5, 1, np.complex64, 1e-5, "uniform"),       # fine grid smaller than one tile
+    (2, (9, 7), 500, 5, 2, np.complex64, 1e-5, "uniform"),
+    (3, (5, 6, 7), 400, 1, 1, np.complex64, 1e-4, "uniform"),
+    (3, (5, 6, 7), 400, 1, 2, np.complex64, 1e-4, "uniform"),
 ]
 
 
