@@ -64,8 +64,11 @@ typedef struct b200nufft_opts {
                               0 = std::thread::hardware_concurrency()                             */
   int bin_dims[3];         /* engine bin geometry (cf. InternalOptions::gpu_bin_size); 0 = auto   */
   int max_subproblem_size; /* points per subproblem (cf. gpu_max_subproblem_size = 1024); 0 = auto */
-  int spread_method;       /* 0 auto, 1 global-atomic point-driven, 2 shared-memory tiles         */
-  int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged)  */
+  int spread_method;       /* 0 auto, 1 global-atomic point-driven, 2 shared-memory tiles,
+                              3 window-sorted register runs, 4 same with even-row windows (2D
+                              type-1 NUFFT plans; falls back to 3 elsewhere)                      */
+  int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged),
+                              3 persistent double-buffered tiles                                  */
   int profile;             /* 1: record CUDA events around the stages (b200nufft_get_timings)     */
   int reserved[8];
 } b200nufft_opts;

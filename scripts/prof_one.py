@@ -18,6 +18,8 @@ else:
 M = pts.shape[0]; N = int(np.prod(grid))
 kw = dict(spread_method=meth, interp_method=min(meth, 2))
 if bins: kw["bin_dims"] = bins
+if os.environ.get("NC"): kw["coils_per_cta"] = int(os.environ["NC"])
+if os.environ.get("TCOILS"): T = int(os.environ["TCOILS"])
 plan = _lib.Plan(ttype, grid[::-1], -1, T, 1e-6, 0, device=0, **kw)
 dp = torch.from_numpy(pts).cuda()
 c = torch.from_numpy(H.random_complex((T, M), 1)).cuda()

@@ -145,6 +145,8 @@ class Plan:
         opts.reserved[0] = int(v)
       elif k == "coils_per_cta":
         opts.reserved[1] = int(v)
+      elif k == "kernel_variant":
+        opts.reserved[2] = int(v)
       else:
         if not hasattr(opts, k):
           raise TypeError(f"unknown option {k}")

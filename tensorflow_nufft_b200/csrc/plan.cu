@@ -25,6 +25,7 @@
 #include "scan_sort.cuh"
 #include "spread.cuh"
 #include "spread_ws.cuh"
+#include "spread_ws2.cuh"
 
 using namespace b200;
 
@@ -79,6 +80,7 @@ struct b200nufft_plan {
   int tmap_batch = 0;
   bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
+  bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
   size_t tile_smem = 0;
 
   // device state
@@ -225,6 +227,28 @@ cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, 
   return cudaGetLastError();
 }
 
+template <int NC>
+cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
+  const size_t smem = spread_ws_smem_bytes<2, NC>(p->bin);
+#define WS2_CASE(NS)                                                                             \
+  case NS: {                                                                                     \
+    auto k = spread_ws2_f32_kernel<NS, NC>;                                                          \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw);                 \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    WS2_CASE(2) WS2_CASE(3) WS2_CASE(4) WS2_CASE(5) WS2_CASE(6) WS2_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef WS2_CASE
+  return cudaGetLastError();
+}
+
 // Builds (or reuses) the TMA tensor map of a fine-grid batch [ntr][nf2][nf1][2*nf0] float32 with a
 // box of one tile. cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -326,7 +350,18 @@ cudaError_t launch_interp_pipe(b200nufft_plan* p, int ntr, const float2* fw, flo
 template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->spread_method == 3) {
+  if (p->spread_method == 4) {
+    cudaError_t e;
+    const float2* cc = static_cast<const float2*>(c);
+    float2* ff = static_cast<float2*>(fw);
+    const int nc_opt = p->opts.reserved[1];   // coils per CTA override (0 = auto)
+    const int nc = nc_opt > 0 ? nc_opt : 8;   // measured on cfg2: 8 coils 1.38 ms, 4 coils 1.45 ms per 32 x 2M
+    if (nc >= 8 && ntr % 8 == 0) e = launch_spread_ws2<8>(p, ntr, cc, ff, st);
+    else if (nc >= 4 && ntr % 4 == 0) e = launch_spread_ws2<4>(p, ntr, cc, ff, st);
+    else if (nc >= 2 && ntr % 2 == 0) e = launch_spread_ws2<2>(p, ntr, cc, ff, st);
+    else e = launch_spread_ws2<1>(p, ntr, cc, ff, st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread ws2 launch: %s", cudaGetErrorString(e));
+  } else if (p->spread_method == 3) {
     cudaError_t e;
     const float2* cc = static_cast<const float2*>(c);
     float2* ff = static_cast<float2*>(fw);
@@ -497,8 +532,9 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   for (int d = 0; d < 3; ++d) { bg.nf[d] = p->nf[d]; bg.bin[d] = p->bin[d]; bg.nbins[d] = p->nbins[d]; }
   bg.ws = p->ws ? 1 : 0;
   bg.WX = p->bin[0] / 2 + 3;
-  bg.WY = p->bin[1] + 7;
+  bg.WY = p->ws2 ? p->bin[1] / 2 + 3 : p->bin[1] + 7;
   bg.align_x = p->is_double ? 0 : 1;
+  bg.align_y = p->ws2 ? 1 : 0;
   const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY : 1);
 
   CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * p->nbtot, st));
@@ -557,12 +593,13 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   p->launches++;
 
   const int align_x = (!p->is_double) ? 1 : 0;
+  const int align = align_x | (p->ws2 ? 2 : 0);
   if (p->PX == 8 && p->PY == 8 && rank >= 2) {
     const F beta = static_cast<F>(p->kp.beta), cc = static_cast<F>(p->kp.c), hw = static_cast<F>(p->kp.half_width);
     if (rank == 2)
       stencil_record8_kernel<F, 2><<<grid_for(M * 2, 256, 16), 256, 0, st>>>(
           M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
-          align_x, p->start.as<int>(), p->wrec.as<F>());
+          align, p->start.as<int>(), p->wrec.as<F>());
     else
       stencil_record8_kernel<F, 3><<<grid_for(M * 3, 256, 16), 256, 0, st>>>(
           M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
@@ -632,18 +669,23 @@ int create_impl(b200nufft_plan* p) {
 
   // ---- method + bin geometry ----
   const bool tile_ok = !p->is_double && ns <= 7 && p->rank >= 2;
-  // auto: 2D -> window-sorted register-accumulating spreader (3); 3D -> plane-owner tile kernel (2)
-  // (measured on B200: cfg2 0.79 vs 1.13 ms per 8 coils; cfg3 3.2 ms tile vs >= 4.0 ms window-sorted)
-  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 3 : 2) : 1) : p->opts.spread_method;
+  // auto: 2D -> window-sorted register-accumulating spreader (4 = even-row windows for NUFFT plans,
+  // 3 for spread-only plans); 3D -> plane-owner tile kernel (2)
+  // (measured on B200, cfg2 per 32 coils: 1.38 ms (4) vs 1.70 ms (3) vs 4.5 ms (2); cfg3: 3.2 ms
+  //  tile vs >= 4.0 ms window-sorted)
+  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 4 : 2) : 1) : p->opts.spread_method;
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 2 : 1) : p->opts.interp_method;
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
+  // ws2 is 2D, type-1 NUFFT plans only (its records are not usable by the other kernels)
+  if (p->spread_method == 4 && (p->rank != 2 || p->type != 1 || p->opts.spread_only)) p->spread_method = 3;
+  const bool ws_any = p->spread_method == 3 || p->spread_method == 4;
   int def_bin[3] = {1, 1, 1};
   if (p->rank == 1) { def_bin[0] = 1024; }
   else if (p->rank == 2) {
     // window-sorted spreader: small tiles (24 x 16 cells) so that 4 coils' tiles + the stage fit
     // ~8 CTAs per SM (measured best on cfg2: 0.48 ms per 8 coils vs 0.79 ms at 32 x 32)
-    def_bin[0] = (p->type == 1 && p->spread_method == 3) ? 16 : 32;
-    def_bin[1] = (p->type == 1 && p->spread_method == 3) ? 8 : 32;
+    def_bin[0] = (p->type == 1 && ws_any) ? 16 : 32;
+    def_bin[1] = (p->type == 1 && ws_any) ? 8 : 32;
   }
   else {
     def_bin[0] = 16;
@@ -659,11 +701,15 @@ int create_impl(b200nufft_plan* p) {
   }
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
-  p->ws = uses_tile && p->type == 1 && p->spread_method == 3;
+  p->ws = uses_tile && p->type == 1 && ws_any;
+  p->ws2 = p->ws && p->spread_method == 4;
+  if (p->ws2 && (p->bin[1] & 1))
+    return set_err(p, B200NUFFT_INVALID_ARGUMENT, "even-row window spreader needs an even bin_dims[1]");
   if (p->ws && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)
     return set_err(p, B200NUFFT_INVALID_ARGUMENT, "window-sorted 3D spreader needs bin_dims[2] of 4 or 8");
   if (p->ws && static_cast<int64_t>(p->nbtot) * (p->bin[0] / 2 + 3) * (p->bin[1] + 7) >= (int64_t(1) << 31)) {
     p->ws = false;
+    p->ws2 = false;
     p->spread_method = 2;
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
@@ -671,7 +717,7 @@ int create_impl(b200nufft_plan* p) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
-    if (uses_tile && p->spread_method == 3) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
+    if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
     if (uses_tile_i && p->interp_method == 3) need = std::max(need, p->rank == 2 ? interp_pipe_smem_bytes<2, kPipeWarps>(p->bin) : interp_pipe_smem_bytes<3, kPipeWarps>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));

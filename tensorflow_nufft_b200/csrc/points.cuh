@@ -53,6 +53,7 @@ struct BinGeom {
   int ws;        // 0: key = bin only
   int WX, WY;
   int align_x;   // stencil x start aligned down to an even cell
+  int align_y;   // stencil y start aligned down to an even row (ws2 spreader): wy counts row pairs
 };
 
 template <typename F>
@@ -114,6 +115,7 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
       int wx = (x0 - (bd[0] * g.bin[0] - 4)) >> 1;
       const int i1y = static_cast<int>(ceil(sub_rn(x[1], half_width)));
       int wy = i1y - (bd[1] * g.bin[1] - 4);
+      if (g.align_y) wy = (i1y - (i1y & 1) - (bd[1] * g.bin[1] - 4)) >> 1;
       wx = wx < 0 ? 0 : (wx >= g.WX ? g.WX - 1 : wx);
       wy = wy < 0 ? 0 : (wy >= g.WY ? g.WY - 1 : wy);
       key = key * (g.WX * g.WY) + wy * g.WX + wx;
@@ -277,11 +279,14 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
 // Fast path of the record kernel for the tile kernels' layout (PX = PY = 8, ns <= 7):
 // one thread per (point, dimension) computes the stencil start once and its 8 weights, and stores
 // them as two 128-bit writes (adjacent threads write adjacent 32-byte chunks: fully coalesced).
+// `align` bit d: the stencil start of dimension d is moved down to an even cell and the weights
+// are shifted by its parity (zero padded); bit 0 is the tile kernels' x alignment, bit 1 the ws2
+// spreader's row alignment.
 template <typename F, int RANK>
 __global__ void __launch_bounds__(256)
 stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restrict__ f0,
                        const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
-                       int align_x, int* __restrict__ start /* int4 per point */, F* __restrict__ wrec) {
+                       int align, int* __restrict__ start /* int4 per point */, F* __restrict__ wrec) {
   const int64_t total = M * RANK;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
@@ -292,7 +297,7 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
     const F x = fd[i];
     const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
     const F x1 = sub_rn(static_cast<F>(i1), x);
-    const int shift = (d == 0 && align_x) ? (i1 & 1) : 0;
+    const int shift = ((align >> d) & 1) ? (i1 & 1) : 0;
     F w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -304,7 +309,7 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
     for (int k = 0; k < 8; ++k) out[k] = w[k];
     int* st = start + 4 * j;
     if (d == 0) { st[0] = i1 - shift; st[3] = shift; if (RANK < 2) st[1] = 0; if (RANK < 3) st[2] = 0; }
-    else st[d] = i1;
+    else st[d] = i1 - shift;
   }
 }
 

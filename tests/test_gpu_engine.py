@@ -230,13 +230,14 @@ def test_tile_and_global_kernels_agree(rank):
   res = {}
   for ttype in (1, 2):
     src = H.random_complex((2, M) if ttype == 1 else (2,) + grid, 42)
-    for meth in (1, 2, 3):
+    for meth in (1, 2, 3, 4):
       out = nufft_ops._run_op(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid, f"type_{ttype}",
                               "forward", 1e-6, None, "nufft",
                               engine_kwargs={"spread_method": meth, "interp_method": meth})
       res[(ttype, meth)] = out.cpu().numpy()
     assert H.rel_l2(res[(ttype, 2)], res[(ttype, 1)]) < 5e-7
     assert H.rel_l2(res[(ttype, 3)], res[(ttype, 1)]) < 5e-7
+    assert H.rel_l2(res[(ttype, 4)], res[(ttype, 1)]) < 5e-7
 
 
 @pytest.mark.parametrize("rank", [2, 3])
