@@ -21,6 +21,7 @@
 #include "dev_common.cuh"
 #include "host_params.h"
 #include "interp.cuh"
+#include "interp_ring.cuh"
 #include "points.cuh"
 #include "scan_sort.cuh"
 #include "spread.cuh"
@@ -347,6 +348,39 @@ cudaError_t launch_interp_pipe(b200nufft_plan* p, int ntr, const float2* fw, flo
   return cudaGetLastError();
 }
 
+constexpr int kRingWarps = 8;
+constexpr int kRingMaxPoints = 256;   // points per subproblem staged in shared memory by the ring kernel
+
+template <int RANK>
+cudaError_t launch_interp_ring(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
+  const size_t smem = interp_ring_smem_bytes<RANK, kRingWarps>(p->bin, p->msub);
+  cudaError_t e = cudaSuccess;
+#define RING_CASE(NS)                                                                            \
+  case NS: {                                                                                     \
+    auto k = interp_ring_f32_kernel<NS, RANK, kRingWarps>;                                       \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    int per_sm = 0;                                                                              \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRingWarps * 32, smem);        \
+    if (e != cudaSuccess) return e;                                                              \
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;                                        \
+    const int64_t cap = static_cast<int64_t>(kNumSMsB200) * per_sm;                              \
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(p->sub_bound, cap))); \
+    k<<<grid, kRingWarps * 32, smem, st>>>(p->M, g, ntr, p->msub, p->sub_total(),                \
+                                           p->sub_desc.as<int4>(), p->idx, p->start.as<int4>(),  \
+                                           p->wrec.as<float4>(), fw, c, p->tmap, use_tma);       \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    RING_CASE(2) RING_CASE(3) RING_CASE(4) RING_CASE(5) RING_CASE(6) RING_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef RING_CASE
+  return cudaGetLastError();
+}
+
 template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
@@ -396,7 +430,12 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
 template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->interp_method == 3) {
+  if (p->interp_method == 4) {
+    cudaError_t e = p->rank == 2
+        ? launch_interp_ring<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
+        : launch_interp_ring<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp ring launch: %s", cudaGetErrorString(e));
+  } else if (p->interp_method == 3) {
     cudaError_t e = p->rank == 2
         ? launch_interp_pipe<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
         : launch_interp_pipe<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
@@ -570,6 +609,8 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     while (ms < 1024 && ms < per_item) ms *= 2;
     p->msub = ms;
   }
+  if (p->interp_method == 4 && (p->type == 2 || p->opts.spread_only))
+    p->msub = std::max(4, std::min(p->msub, kRingMaxPoints) & ~3);
   if (p->nbtot <= kScanSmallMax) {
     scan_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
                                          p->sub_total());
@@ -690,7 +731,7 @@ int create_impl(b200nufft_plan* p) {
   else {
     def_bin[0] = 16;
     def_bin[1] = 16;
-    def_bin[2] = (p->type == 2) ? 2 : (p->spread_method == 3 ? 8 : 2);
+    def_bin[2] = (p->type == 2) ? (p->interp_method == 4 ? 8 : 2) : (p->spread_method == 3 ? 8 : 2);
     if (p->type == 1 && p->spread_method == 3) def_bin[1] = 8;
   }
   p->nbtot = 1;
@@ -719,7 +760,8 @@ int create_impl(b200nufft_plan* p) {
     size_t need = 0;
     if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
-    if (uses_tile_i && p->interp_method == 3) need = std::max(need, p->rank == 2 ? interp_pipe_smem_bytes<2, kPipeWarps>(p->bin) : interp_pipe_smem_bytes<3, kPipeWarps>(p->bin));
+    if (uses_tile_i && p->interp_method == 4) need = std::max(need, p->rank == 2 ? interp_ring_smem_bytes<2, kRingWarps>(p->bin, kRingMaxPoints) : interp_ring_smem_bytes<3, kRingWarps>(p->bin, kRingMaxPoints));
+    else if (uses_tile_i && p->interp_method == 3) need = std::max(need, p->rank == 2 ? interp_pipe_smem_bytes<2, kPipeWarps>(p->bin) : interp_pipe_smem_bytes<3, kPipeWarps>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)
