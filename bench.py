@@ -232,12 +232,14 @@ def run_ours(args, cfg, rank_id, world, device):
                  "l2": "inputs larger than L2 (no flush needed)" if h2d > 126e6 else "working set below L2 size",
                  "step": "set_points + execute, all coils"},
       "stages_ms": {k: round(v, 4) for k, v in stage.items()},
-      "roofline": {"bound": "hbm", "kernel": ("spread_ws_f32_kernel" if rank == 2 else "spread_tile_f32_kernel") if ttype == 1 else "interp_tile_f32_kernel",
+      "roofline": {"bound": "hbm", "kernel": ("spread_ws2_f32_kernel" if rank == 2 else "spread_tile_f32_kernel") if ttype == 1 else "interp_qw_f32_kernel",
                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,
                    "launches_per_step": n_launch,
-                   "note": "type-1 spreading is bound by shared-memory read-modify-write bandwidth, not HBM"},
+                   "note": ("type-1 spreading is bound by shared-memory read-modify-write bandwidth, not HBM" if ttype == 1 else
+                            "type-2 gathering is bound by shared-memory load bandwidth (ns^d cells per point) and, for sparse "
+                            "point sets, by L2->shared tile traffic, not HBM")},
       "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
               "ms_per_step": ms_e2e / args.steps},
       "gpu_launches": int(launches),

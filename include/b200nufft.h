@@ -68,7 +68,8 @@ typedef struct b200nufft_opts {
                               3 window-sorted register runs, 4 same with even-row windows (2D
                               type-1 NUFFT plans; falls back to 3 elsewhere)                      */
   int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged),
-                              3 persistent double-buffered tiles                                  */
+                              lanes over one point's stencil, 3 shared-memory tiles, quarter warp
+                              per point                                                           */
   int profile;             /* 1: record CUDA events around the stages (b200nufft_get_timings)     */
   int reserved[8];
 } b200nufft_opts;

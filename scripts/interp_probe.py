@@ -51,24 +51,24 @@ if __name__ == "__main__":
     q = rng.uniform(-np.pi, np.pi, (50000, 2)).astype(np.float32)
     q[:64, 0] = np.float32(np.pi); q[64:128, 1] = -np.float32(np.pi); q[128:160] = 0
     for tol in (1e-6, 1e-3):
-      run(f"odd2d-130x94-tol{tol}", (94, 130), q, 3, [dict(method=1), dict(method=2), dict(method=4), dict(method=4, no_tma=1), dict(method=4, msub=8)], reps=2, tol=tol)
+      run(f"odd2d-130x94-tol{tol}", (94, 130), q, 3, [dict(method=1), dict(method=2), dict(method=5), dict(method=5, no_tma=1), dict(method=5, msub=8), dict(method=5, bins=(16, 16)), dict(method=4), dict(method=4, no_tma=1), dict(method=4, msub=8)], reps=2, tol=tol)
     q3 = rng.uniform(-np.pi, np.pi, (40000, 3)).astype(np.float32)
     q3[:64, 0] = np.float32(np.pi); q3[64:128, 2] = -np.float32(np.pi); q3[128:160] = 0
     for tol in (1e-6, 1e-2):
-      run(f"odd3d-30x44x26-tol{tol}", (26, 44, 30), q3, 3, [dict(method=1), dict(method=2), dict(method=4), dict(method=4, no_tma=1), dict(method=4, bins=(16, 16, 2)), dict(method=4, bins=(16, 8, 4), msub=12)], reps=2, tol=tol)
-    run("ext-range3d", (32, 32, 32), (q3 * 2.9).astype(np.float32), 2, [dict(method=1), dict(method=2), dict(method=4)], reps=2)
+      run(f"odd3d-30x44x26-tol{tol}", (26, 44, 30), q3, 3, [dict(method=1), dict(method=2), dict(method=5), dict(method=5, no_tma=1), dict(method=5, bins=(16, 16, 8)), dict(method=5, bins=(16, 8, 4), msub=12), dict(method=4), dict(method=4, no_tma=1), dict(method=4, bins=(16, 8, 4), msub=12)], reps=2, tol=tol)
+    run("ext-range3d", (32, 32, 32), (q3 * 2.9).astype(np.float32), 2, [dict(method=1), dict(method=2), dict(method=5)], reps=2)
   if "cfg4" in which:
     p = H.stack_of_stars_points(125, 125, 256)
     run("cfg4-sos-256-T2", (256, 256, 256), p, 2,
-        [dict(method=2), dict(method=4), dict(method=4, bins=(16, 16, 4)), dict(method=4, bins=(16, 16, 2)),
-         dict(method=4, bins=(16, 8, 8)), dict(method=4, bins=(32, 16, 4)), dict(method=4, msub=128)])
+        [dict(method=5), dict(method=4), dict(method=4, bins=(16, 16, 4)), dict(method=4, bins=(16, 16, 8)),
+         dict(method=4, bins=(16, 8, 4)), dict(method=4, bins=(16, 8, 2)), dict(method=5, bins=(16, 8, 2))])
   if "cfg3" in which:
     p = H.uniform_points(8000000, 3, 3)
     run("cfg3-uniform-128-type2", (128, 128, 128), p, 1,
-        [dict(method=2), dict(method=4), dict(method=4, bins=(16, 16, 4)), dict(method=4, bins=(16, 8, 8))])
+        [dict(method=5), dict(method=5, bins=(16, 8, 4)), dict(method=4), dict(method=4, bins=(16, 8, 4)), dict(method=5, bins=(16, 8, 2)), dict(method=5, bins=(16, 8, 8))])
   if "cfg2" in which:
     p = H.spiral_points(32, 62500)
     run("cfg2-spiral-512-T8-type2", (512, 512), p, 8,
-        [dict(method=2), dict(method=4), dict(method=4, bins=(16, 16)), dict(method=4, bins=(32, 16)), dict(method=4, bins=(64, 32))])
+        [dict(method=5), dict(method=4), dict(method=4, bins=(16, 16))])
   if "cfg1" in which:
-    run("cfg1-radial-256", (256, 256), H.radial_points(200, 500), 1, [dict(method=2), dict(method=4), dict(method=4, bins=(16, 16))])
+    run("cfg1-radial-256", (256, 256), H.radial_points(200, 500), 1, [dict(method=2), dict(method=5), dict(method=5, bins=(16, 16))])

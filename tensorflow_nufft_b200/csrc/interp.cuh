@@ -290,239 +290,6 @@ interp_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Persistent, double-buffered variant. grid = a few CTAs per SM; each CTA walks the work items
-// (subproblem, transform) with a static stride and keeps TWO tile buffers: while the warps gather
-// from tile i, one thread has already issued the TMA box copy of tile i+1 into the other buffer
-// (or all threads their cp.async copies, for tiles that straddle the periodic boundary), and every
-// lane has already fetched its record of item i+1's first batch into registers. The tile-load
-// latency that dominates sparse point sets (stack-of-stars: ~40 points per 46 KB tile) is hidden.
-// ---------------------------------------------------------------------------------------------
-template <int NS, int RANK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-interp_pipe_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__ sub_total,
-                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
-                       const int4* __restrict__ start, const float4* __restrict__ wrec4,
-                       const float2* __restrict__ fw, float2* __restrict__ c,
-                       const __grid_constant__ CUtensorMap tmap, int use_tma) {
-  constexpr int QX = (NS + 2) / 2;
-  constexpr int C4 = 2 * RANK;
-  constexpr int SW = StageRec<RANK>::kWords;
-  extern __shared__ __align__(128) float4 smem4[];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int TX = g.bin[0] + 8, TY = g.bin[1] + 8;
-  const int TZ = RANK > 2 ? g.bin[2] + 8 : 1;
-  const int ncell = TX * TY * TZ;
-  const int TXH = TX / 2;
-  const int tile_f4 = (ncell / 2 + 7) & ~7;                         // 128-byte aligned tile pitch
-  float4* tiles = smem4;                                            // [2][tile_f4]
-  float* stage = reinterpret_cast<float*>(smem4 + 2 * tile_f4) + warp * 32 * SW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem4 + 2 * tile_f4) + WARPS * 32 * SW);
-
-  const int nsub = *sub_total;
-  const int64_t nitems = static_cast<int64_t>(nsub) * ntr;
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-  __syncthreads();
-
-  const int q = lane % QX;
-  const int r = lane / QX;
-  const bool row_ok = r < NS;
-  const int lane_off = r * TX + 2 * q;
-  const int zstride4 = TY * TX / 2;
-
-  struct Item { int t, p0, np, ox, oy, oz; bool interior; };
-  auto decode = [&](int64_t w) {
-    Item it;
-    it.t = static_cast<int>(w / nsub);
-    const int4 sd = sub_desc[static_cast<int>(w - static_cast<int64_t>(it.t) * nsub)];
-    const int b = sd.x;
-    it.p0 = sd.y;
-    it.np = sd.z;
-    const int bx = b % g.nbins[0];
-    const int by = (b / g.nbins[0]) % g.nbins[1];
-    const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
-    it.ox = bx * g.bin[0] - 4;
-    it.oy = by * g.bin[1] - 4;
-    it.oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
-    it.interior = use_tma && it.ox >= 0 && it.ox + TX <= g.nf[0] && it.oy >= 0 && it.oy + TY <= g.nf[1] &&
-                  (RANK < 3 || (it.oz >= 0 && it.oz + TZ <= g.nf[2]));
-    return it;
-  };
-  // Starts the copy of one tile into buffer `buf` (does not wait).
-  auto issue_tile = [&](const Item& it, int buf) {
-    float4* dst = tiles + buf * tile_f4;
-    if (it.interior) {
-      if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this buffer are done
-        mbar_expect_tx(&bars[buf], static_cast<uint32_t>(ncell * sizeof(float2)));
-        if (RANK == 2) tma_load_3d(dst, &tmap, &bars[buf], 2 * it.ox, it.oy, it.t);
-        else tma_load_4d(dst, &tmap, &bars[buf], 2 * it.ox, it.oy, it.oz, it.t);
-      }
-    } else {
-      const float2* fwt = fw + static_cast<int64_t>(it.t) * g.nftot;
-      for (int i = tid; i < ncell / 2; i += WARPS * 32) {
-        const int ix = i % TXH;
-        const int iy = (i / TXH) % TY;
-        const int iz = i / (TXH * TY);
-        const int gx = mod_idx(it.ox + 2 * ix, g.nf[0]);
-        const int gy = mod_idx(it.oy + iy, g.nf[1]);
-        const int gz = RANK > 2 ? mod_idx(it.oz + iz, g.nf[2]) : 0;
-        __pipeline_memcpy_async(&dst[i], fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx, 16);
-      }
-    }
-    __pipeline_commit();   // (empty group for TMA tiles: keeps the group count uniform)
-  };
-
-  float4 w4[C4];
-  int4 st_n = make_int4(0, 0, 0, 0);
-  int id_n = 0;
-  auto fetch = [&](const Item& it, int first) {
-    const int pl = first + lane;
-    if (pl < it.np) {
-      const int64_t j = it.p0 + pl;
-#pragma unroll
-      for (int k = 0; k < C4; ++k) w4[k] = wrec4[j * C4 + k];
-      st_n = start[j];
-      id_n = idx[j];
-    }
-  };
-
-  int64_t w = blockIdx.x;
-  if (w >= nitems) return;
-  Item cur = decode(w);
-  issue_tile(cur, 0);
-  fetch(cur, warp * 32);
-  uint32_t phase[2] = {0u, 0u};
-  int buf = 0;
-  while (true) {
-    const int64_t wn = w + gridDim.x;
-    const bool has_next = wn < nitems;
-    Item nxt = cur;
-    if (has_next) {
-      nxt = decode(wn);
-      issue_tile(nxt, buf ^ 1);
-    }
-    // ---- wait for the current tile ----
-    if (cur.interior) {
-      mbar_wait(&bars[buf], phase[buf]);
-      phase[buf] ^= 1u;
-    } else {
-      if (has_next) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-      __syncthreads();
-    }
-    const float2* tile = reinterpret_cast<const float2*>(tiles + buf * tile_f4);
-    float2* ct = c + static_cast<int64_t>(cur.t) * M;
-
-    for (int first = warp * 32; first < cur.np; first += WARPS * 32) {
-      const int id_cur = id_n;
-      {
-        const int pl = first + lane;
-        float4* rec4 = reinterpret_cast<float4*>(stage + lane * SW);
-        int off = -1;
-        if (pl < cur.np) {
-          const int rx = st_n.x - cur.ox, ry = st_n.y - cur.oy, rz = RANK > 2 ? st_n.z - cur.oz : 0;
-          const bool fits = rx >= 0 && rx + 2 * QX <= TX && ry >= 0 && ry + NS <= TY &&
-                            (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
-          if (fits) off = (rz * TY + ry) * TX + rx;
-        }
-#pragma unroll
-        for (int k = 0; k < C4; ++k) rec4[k] = w4[k];
-        rec4[6] = make_float4(__int_as_float(off), 0.f, 0.f, 0.f);
-      }
-      __syncwarp();
-      // prefetch: next batch of this item, or the first batch of the next item
-      if (first + WARPS * 32 < cur.np) fetch(cur, first + WARPS * 32);
-      else if (has_next) fetch(nxt, warp * 32);
-
-      float2 res_l = make_float2(0.f, 0.f);
-      const int cnt = min(32, cur.np - first);
-      for (int p4 = 0; p4 < cnt; p4 += 4) {
-        float re[4], im[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          re[u] = 0.f;
-          im[u] = 0.f;
-          const int p = p4 + u;
-          if (p < cnt) {
-            const float* rec = stage + p * SW;
-            const int off = __float_as_int(rec[24]);
-            if (row_ok && off >= 0) {
-              const float2 wx = *reinterpret_cast<const float2*>(rec + 2 * q);
-              const float wy = rec[8 + r];
-              const float4* ptr = reinterpret_cast<const float4*>(tile + off + lane_off);
-              if (RANK == 2) {
-                const float4 v = *ptr;
-                re[u] = wy * (v.x * wx.x + v.z * wx.y);
-                im[u] = wy * (v.y * wx.x + v.w * wx.y);
-              } else {
-                float4 v[NS];
-#pragma unroll
-                for (int dz = 0; dz < NS; ++dz) v[dz] = ptr[dz * zstride4];
-                float wz[8];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 t2 = *reinterpret_cast<const float2*>(rec + 16 + 2 * k);
-                  wz[2 * k] = t2.x;
-                  wz[2 * k + 1] = t2.y;
-                }
-                float ar = 0.f, ai = 0.f;
-#pragma unroll
-                for (int dz = 0; dz < NS; ++dz) {
-                  ar += wz[dz] * (v[dz].x * wx.x + v[dz].z * wx.y);
-                  ai += wz[dz] * (v[dz].y * wx.x + v[dz].w * wx.y);
-                }
-                re[u] = ar * wy;
-                im[u] = ai * wy;
-              }
-            }
-          }
-        }
-        {
-          const bool hi16 = lane & 16, hi8 = lane & 8;
-          float a0 = hi16 ? re[0] : re[1], k0 = hi16 ? re[1] : re[0];
-          float a1 = hi16 ? re[2] : re[3], k1 = hi16 ? re[3] : re[2];
-          k0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-          k1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-          float a2 = hi8 ? k0 : k1, kr = hi8 ? k1 : k0;
-          kr += __shfl_xor_sync(0xffffffffu, a2, 8);
-          float b0 = hi16 ? im[0] : im[1], m0 = hi16 ? im[1] : im[0];
-          float b1 = hi16 ? im[2] : im[3], m1 = hi16 ? im[3] : im[2];
-          m0 += __shfl_xor_sync(0xffffffffu, b0, 16);
-          m1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-          float b2 = hi8 ? m0 : m1, ki = hi8 ? m1 : m0;
-          ki += __shfl_xor_sync(0xffffffffu, b2, 8);
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
-            kr += __shfl_xor_sync(0xffffffffu, kr, o);
-            ki += __shfl_xor_sync(0xffffffffu, ki, o);
-          }
-          const int src_lane = ((lane - p4) & 1 ? 16 : 0) | ((lane - p4) & 2 ? 8 : 0);
-          const float rr = __shfl_sync(0xffffffffu, kr, src_lane);
-          const float ri = __shfl_sync(0xffffffffu, ki, src_lane);
-          if (lane >= p4 && lane < p4 + 4) res_l = make_float2(rr, ri);
-        }
-      }
-      if (first + lane < cur.np) ct[id_cur] = res_l;
-      __syncwarp();
-    }
-    // warps that had no batch in this item still owe the prefetch of the next item's first batch
-    if (warp * 32 >= cur.np && has_next) fetch(nxt, warp * 32);
-    if (!has_next) break;
-    __syncthreads();   // everyone is done with tile `buf` before it is refilled two items later
-    cur = nxt;
-    w = wn;
-    buf ^= 1;
-  }
-}
-
-template <int RANK, int WARPS>
-inline size_t interp_pipe_smem_bytes(const int* bin) {
-  const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
-  const size_t tile_f4 = (ncell / 2 + 7) & ~static_cast<size_t>(7);
-  return 2 * tile_f4 * sizeof(float4) + static_cast<size_t>(WARPS) * 32 * StageRec<RANK>::kWords * sizeof(float) + 32;
-}
-
 template <int RANK, int WARPS>
 inline size_t interp_tile_smem_bytes(const int* bin) {
   const size_t ncell = static_cast<size_t>(bin[0] + 8) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);

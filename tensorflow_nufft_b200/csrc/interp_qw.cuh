@@ -1,0 +1,177 @@
+// interp_qw.cuh -- type-2 interpolator, quarter-warp-per-point gather from a shared-memory tile.
+//
+// Same sums as interp.cuh (reference: InterpSubproblem{2,3}DKernel nufft_plan.cu.cc:1041-1110,
+// 1608-1706). interp_tile_f32_kernel lays the 32 lanes of a warp over ONE point's stencil and pays
+// a 5-level butterfly per point; here a warp works on FOUR points at once: the 8 lanes of a
+// quarter warp take the 8 rows of one point's window and each lane walks its row (8 cells = four
+// 128-bit shared loads per z-plane). Per point this costs
+//   * the same tile traffic (the stencil's bytes, inherent),
+//   * a quarter of the instructions (every warp instruction serves 4 points),
+//   * 1.5 shuffles instead of 4.5 (3-level reduction inside the quarter, re and im),
+//   * no shared-memory staging of the records at all: a lane reads its point's weights straight
+//     from the sorted record array (8 lanes share each 16-byte load), prefetched one group ahead.
+// The tile pitch is bin_x + 10 cells = 2 * odd mod 16, which makes the 8 row-lanes of a quarter
+// warp hit 8 distinct 16-byte bank groups: every 128-bit load is conflict-free.
+#pragma once
+#include <cuda.h>
+#include <cuda_pipeline.h>
+
+#include "dev_common.cuh"
+#include "interp.cuh"
+#include "spread.cuh"
+
+namespace b200 {
+
+constexpr int kQwHaloX = 10;   // tile x extent = bin_x + 10 (stencil reach 8 + 2 pad cells for the pitch)
+
+template <int RANK>
+inline size_t interp_qw_smem_bytes(const int* bin) {
+  const size_t ncell = static_cast<size_t>(bin[0] + kQwHaloX) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
+  return ((ncell * sizeof(float2) + 127) & ~static_cast<size_t>(127)) + 16;
+}
+
+// Gathers the points [0, np) of one subproblem from `tile4` (origin ox, oy, oz; pitch TX cells).
+// Groups of 4 points are dealt round-robin to the `nwarps` warps. Records are read from global
+// memory (sorted order, base index p0).
+template <int NS, int RANK, typename WaitTile>
+__device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __restrict__ tile4, int TX, int TY, int TZ, int ox, int oy, int oz,
+                                          int p0, int np, int warp, int nwarps, int lane,
+                                          const int* __restrict__ idx, const int4* __restrict__ start,
+                                          const float4* __restrict__ wrec4, float2* __restrict__ ct) {
+  constexpr int C4 = 2 * RANK;
+  const int pt = lane >> 3;
+  const int row = lane & 7;
+  const int zstride4 = TY * TX / 2;
+  const int ngrp = (np + 3) >> 2;
+
+  float4 wxa, wxb, wza, wzb;
+  float wy = 0.f;
+  int4 st = make_int4(0, 0, 0, 0);
+  int id = 0;
+  wxa = wxb = wza = wzb = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int grp) {
+    const int p = 4 * grp + pt;
+    if (grp < ngrp && p < np) {
+      const int64_t j = static_cast<int64_t>(p0) + p;
+      wxa = wrec4[j * C4];
+      wxb = wrec4[j * C4 + 1];
+      wy = reinterpret_cast<const float*>(wrec4 + j * C4 + 2)[row];
+      if (RANK > 2) {
+        wza = wrec4[j * C4 + 4];
+        wzb = wrec4[j * C4 + 5];
+      }
+      st = start[j];
+      id = idx[j];
+    }
+  };
+  fetch(warp);
+  wait_tile();   // the first records are in flight while the tile lands
+  for (int grp = warp; grp < ngrp; grp += nwarps) {
+    const float4 xa = wxa, xb = wxb, za = wza, zb = wzb;
+    const float wy_c = wy;
+    const int4 st_c = st;
+    const int id_c = id;
+    fetch(grp + nwarps);
+
+    const bool valid = 4 * grp + pt < np;
+    float re = 0.f, im = 0.f;
+    const int rx = st_c.x - ox, ry = st_c.y - oy, rz = RANK > 2 ? st_c.z - oz : 0;
+    // Memory safety for coordinates outside the declared points_range (see interp.cuh).
+    const bool fits = rx >= 0 && rx + 8 <= TX && ry >= 0 && ry + NS <= TY && (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
+    if (valid && fits && row < NS) {
+      const float4* ptr = tile4 + (((rz * TY + ry + row) * TX + rx) >> 1);
+      if (RANK == 2) {
+        const float4 v0 = ptr[0], v1 = ptr[1], v2 = ptr[2], v3 = ptr[3];
+        re = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
+        im = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
+      } else {
+        const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+        for (int dz = 0; dz < NS; ++dz) {
+          const float4* pz = ptr + dz * zstride4;
+          const float4 v0 = pz[0], v1 = pz[1], v2 = pz[2], v3 = pz[3];
+          const float pr = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
+          const float pi = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
+          re += wz[dz] * pr;
+          im += wz[dz] * pi;
+        }
+      }
+      re *= wy_c;
+      im *= wy_c;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (valid && row == 0) ct[id_c] = make_float2(re, im);
+  }
+}
+
+// One CTA (WARPS warps) per (subproblem, transform); tile staged by ONE TMA box copy (interior) or
+// wrapped 16-byte cp.async copies (tiles that straddle the periodic boundary); the other resident
+// CTAs of the SM hide the tile latency. (A persistent grid-stride variant and a two-stage tile ring
+// were measured slower on every BASELINE config: static striding loses the hardware scheduler's
+// load balancing between heavy and light subproblems.)
+template <int NS, int RANK, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
+                     const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                     const int4* __restrict__ start, const float4* __restrict__ wrec4,
+                     const float2* __restrict__ fw, float2* __restrict__ c,
+                     const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) float4 smem4[];
+  const int s = blockIdx.x;
+  if (s >= *sub_total) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.y;
+  const int4 sd = sub_desc[s];
+  const int b = sd.x, p0 = sd.y, np = sd.z;
+
+  const int TX = g.bin[0] + kQwHaloX, TY = g.bin[1] + 8;
+  const int TZ = RANK > 2 ? g.bin[2] + 8 : 1;
+  const int bx = b % g.nbins[0];
+  const int by = (b / g.nbins[0]) % g.nbins[1];
+  const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
+  const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = RANK > 2 ? bz * g.bin[2] - 4 : 0;
+  const int ncell = TX * TY * TZ;
+  const int TXH = TX / 2;
+  float4* tile4 = smem4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem4) + ((static_cast<size_t>(ncell) * sizeof(float2) + 127) & ~static_cast<size_t>(127)));
+
+  const float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+  const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
+                        (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]));
+  if (interior) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, static_cast<uint32_t>(ncell * sizeof(float2)));
+      if (RANK == 2) tma_load_3d(tile4, &tmap, bar, 2 * ox, oy, t);
+      else tma_load_4d(tile4, &tmap, bar, 2 * ox, oy, oz, t);
+    }
+  } else {
+    for (int i = tid; i < ncell / 2; i += WARPS * 32) {
+      const int ix = i % TXH;
+      const int iy = (i / TXH) % TY;
+      const int iz = i / (TXH * TY);
+      const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
+      const int gy = mod_idx(oy + iy, g.nf[1]);
+      const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
+      __pipeline_memcpy_async(&tile4[i], fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx, 16);
+    }
+    __pipeline_commit();
+  }
+  auto wait_tile = [&]() {
+    if (interior) {
+      mbar_wait(bar, 0);
+    } else {
+      __pipeline_wait_prior(0);
+      __syncthreads();
+    }
+  };
+  qw_gather<NS, RANK>(wait_tile, tile4, TX, TY, TZ, ox, oy, oz, p0, np, warp, WARPS, lane, idx, start, wrec4,
+                      c + static_cast<int64_t>(t) * M);
+}
+
+}  // namespace b200

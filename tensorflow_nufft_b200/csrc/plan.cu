@@ -21,7 +21,7 @@
 #include "dev_common.cuh"
 #include "host_params.h"
 #include "interp.cuh"
-#include "interp_ring.cuh"
+#include "interp_qw.cuh"
 #include "points.cuh"
 #include "scan_sort.cuh"
 #include "spread.cuh"
@@ -79,6 +79,7 @@ struct b200nufft_plan {
   CUtensorMap tmap;        // TMA descriptor of the fine grid (type-2 tile interpolator)
   const void* tmap_ptr = nullptr;
   int tmap_batch = 0;
+  int tmap_halo = 0;
   bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
@@ -255,8 +256,8 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
-  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr) return true;
+bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8) {
+  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == halo_x) return true;
   static EncodeTiledFn encode = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -274,7 +275,7 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
   cuuint64_t strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   dims[0] = 2ull * p->nf[0];
-  box[0] = 2u * (p->bin[0] + 8);
+  box[0] = 2u * (p->bin[0] + halo_x);
   cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 8;
   for (int d = 1; d < rank; ++d) {
     dims[d] = p->nf[d];
@@ -292,6 +293,7 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
   if (r != CUDA_SUCCESS) return false;
   p->tmap_ptr = grid;
   p->tmap_batch = ntr;
+  p->tmap_halo = halo_x;
   p->tma_ok = true;
   return true;
 }
@@ -320,64 +322,29 @@ cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, flo
   return cudaGetLastError();
 }
 
-constexpr int kPipeWarps = 2;
+constexpr int kQwWarps = 4;
 
 template <int RANK>
-cudaError_t launch_interp_pipe(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
-  const size_t smem = interp_pipe_smem_bytes<RANK, kPipeWarps>(p->bin);
-  const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
-  const int64_t want = static_cast<int64_t>(p->sub_bound) * ntr;
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(kNumSMsB200) * per_sm)));
-#define PIPE_CASE(NS)                                                                            \
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, kQwHaloX)) ? 1 : 0;
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = interp_qw_smem_bytes<RANK>(p->bin);
+#define QW_CASE(NS)                                                                              \
   case NS: {                                                                                     \
-    auto k = interp_pipe_f32_kernel<NS, RANK, kPipeWarps>;                                       \
+    auto k = interp_qw_f32_kernel<NS, RANK, kQwWarps>;                                           \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    k<<<grid, kPipeWarps * 32, smem, st>>>(p->M, g, ntr, p->sub_total(), p->sub_desc.as<int4>(), \
-                                           p->idx, p->start.as<int4>(), p->wrec.as<float4>(),    \
-                                           fw, c, p->tmap, use_tma);                             \
+    k<<<grid, kQwWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),        \
+                                         p->idx, p->start.as<int4>(), p->wrec.as<float4>(),      \
+                                         fw, c, p->tmap, use_tma);                               \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
-    PIPE_CASE(2) PIPE_CASE(3) PIPE_CASE(4) PIPE_CASE(5) PIPE_CASE(6) PIPE_CASE(7)
+    QW_CASE(2) QW_CASE(3) QW_CASE(4) QW_CASE(5) QW_CASE(6) QW_CASE(7)
     default: return cudaErrorInvalidValue;
   }
-#undef PIPE_CASE
-  return cudaGetLastError();
-}
-
-constexpr int kRingWarps = 8;
-constexpr int kRingMaxPoints = 256;   // points per subproblem staged in shared memory by the ring kernel
-
-template <int RANK>
-cudaError_t launch_interp_ring(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
-  GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
-  const size_t smem = interp_ring_smem_bytes<RANK, kRingWarps>(p->bin, p->msub);
-  cudaError_t e = cudaSuccess;
-#define RING_CASE(NS)                                                                            \
-  case NS: {                                                                                     \
-    auto k = interp_ring_f32_kernel<NS, RANK, kRingWarps>;                                       \
-    if (smem > 48 * 1024)                                                                        \
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    int per_sm = 0;                                                                              \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRingWarps * 32, smem);        \
-    if (e != cudaSuccess) return e;                                                              \
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;                                        \
-    const int64_t cap = static_cast<int64_t>(kNumSMsB200) * per_sm;                              \
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(p->sub_bound, cap))); \
-    k<<<grid, kRingWarps * 32, smem, st>>>(p->M, g, ntr, p->msub, p->sub_total(),                \
-                                           p->sub_desc.as<int4>(), p->idx, p->start.as<int4>(),  \
-                                           p->wrec.as<float4>(), fw, c, p->tmap, use_tma);       \
-    break;                                                                                       \
-  }
-  switch (p->kp.ns) {
-    RING_CASE(2) RING_CASE(3) RING_CASE(4) RING_CASE(5) RING_CASE(6) RING_CASE(7)
-    default: return cudaErrorInvalidValue;
-  }
-#undef RING_CASE
+#undef QW_CASE
   return cudaGetLastError();
 }
 
@@ -430,16 +397,11 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
 template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->interp_method == 4) {
+  if (p->interp_method >= 3) {
     cudaError_t e = p->rank == 2
-        ? launch_interp_ring<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
-        : launch_interp_ring<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
-    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp ring launch: %s", cudaGetErrorString(e));
-  } else if (p->interp_method == 3) {
-    cudaError_t e = p->rank == 2
-        ? launch_interp_pipe<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
-        : launch_interp_pipe<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
-    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp pipe launch: %s", cudaGetErrorString(e));
+        ? launch_interp_qw<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
+        : launch_interp_qw<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp qw launch: %s", cudaGetErrorString(e));
   } else if (p->interp_method == 2) {
     cudaError_t e = p->rank == 2
         ? launch_interp_tile<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
@@ -609,8 +571,6 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     while (ms < 1024 && ms < per_item) ms *= 2;
     p->msub = ms;
   }
-  if (p->interp_method == 4 && (p->type == 2 || p->opts.spread_only))
-    p->msub = std::max(4, std::min(p->msub, kRingMaxPoints) & ~3);
   if (p->nbtot <= kScanSmallMax) {
     scan_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
                                          p->sub_total());
@@ -715,7 +675,9 @@ int create_impl(b200nufft_plan* p) {
   // (measured on B200, cfg2 per 32 coils: 1.38 ms (4) vs 1.70 ms (3) vs 4.5 ms (2); cfg3: 3.2 ms
   //  tile vs >= 4.0 ms window-sorted)
   p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 4 : 2) : 1) : p->opts.spread_method;
-  p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 2 : 1) : p->opts.interp_method;
+  // interpolator: 3 = quarter-warp gather (measured: cfg2-type2 0.56 vs 0.92 ms per 8 coils, cfg3-type2
+  // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
+  p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
   // ws2 is 2D, type-1 NUFFT plans only (its records are not usable by the other kernels)
   if (p->spread_method == 4 && (p->rank != 2 || p->type != 1 || p->opts.spread_only)) p->spread_method = 3;
@@ -727,12 +689,14 @@ int create_impl(b200nufft_plan* p) {
     // ~8 CTAs per SM (measured best on cfg2: 0.48 ms per 8 coils vs 0.79 ms at 32 x 32)
     def_bin[0] = (p->type == 1 && ws_any) ? 16 : 32;
     def_bin[1] = (p->type == 1 && ws_any) ? 8 : 32;
+    if (p->type == 2 && p->interp_method == 3) { def_bin[0] = 16; def_bin[1] = 16; }   // cfg2-type2 0.559 vs 0.565 ms, cfg1 12 vs 14 us
   }
   else {
     def_bin[0] = 16;
     def_bin[1] = 16;
-    def_bin[2] = (p->type == 2) ? (p->interp_method == 4 ? 8 : 2) : (p->spread_method == 3 ? 8 : 2);
+    def_bin[2] = (p->type == 2) ? 2 : (p->spread_method == 3 ? 8 : 2);
     if (p->type == 1 && p->spread_method == 3) def_bin[1] = 8;
+    if (p->type == 2 && p->interp_method == 3) def_bin[1] = 8;   // cfg3-type2 1.18 vs 1.35 ms at 16 x 16 x 2
   }
   p->nbtot = 1;
   for (int d = 0; d < 3; ++d) {
@@ -760,8 +724,7 @@ int create_impl(b200nufft_plan* p) {
     size_t need = 0;
     if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
-    if (uses_tile_i && p->interp_method == 4) need = std::max(need, p->rank == 2 ? interp_ring_smem_bytes<2, kRingWarps>(p->bin, kRingMaxPoints) : interp_ring_smem_bytes<3, kRingWarps>(p->bin, kRingMaxPoints));
-    else if (uses_tile_i && p->interp_method == 3) need = std::max(need, p->rank == 2 ? interp_pipe_smem_bytes<2, kPipeWarps>(p->bin) : interp_pipe_smem_bytes<3, kPipeWarps>(p->bin));
+    if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin) : interp_qw_smem_bytes<3>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)
