@@ -264,29 +264,32 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
   dcode = _lib.COMPLEX64 if source.dtype == torch.complex64 else _lib.COMPLEX128
   sign = -1 if fft_direction == "forward" else 1
   chunk = _HOST_CHUNK
+  # Chunk schedule: full chunks, then the last full chunk's worth is halved so that the part of the
+  # pipeline that cannot overlap (the last transform + its D2H copy) is short.
+  sizes = [chunk] * (T // chunk)
+  if T % chunk:
+    sizes.append(T % chunk)
+  if len(sizes) >= 2 and sizes[-1] == chunk and chunk % 2 == 0:
+    sizes[-1:] = [chunk // 2, chunk // 2]
   with torch.cuda.device(dev_index):
     main = torch.cuda.current_stream()
     copy_in, copy_out = _side_streams(dev_index)
-    pts = points.to(device, non_blocking=True).reshape(num_points, -1)
-    plan = _get_plan((ttype, tuple(reversed(grid_shape)), sign, chunk, _op_tol(tol), dcode, dev_index), opt_kwargs)
-    rem = T % chunk
-    plan_rem = None
-    if rem:
-      plan_rem = _get_plan((ttype, tuple(reversed(grid_shape)), sign, rem, _op_tol(tol), dcode, dev_index), opt_kwargs)
-    plan.set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
-    if plan_rem is not None:
-      plan_rem.set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
     d_in = [torch.empty((chunk, src_elems), dtype=source.dtype, device=device) for _ in range(2)]
     d_out = [torch.empty((chunk, tgt_elems), dtype=source.dtype, device=device) for _ in range(2)]
+    # The first strengths copy may start as soon as the buffers exist: it overlaps the points copy
+    # and set_points (bin-sort + stencil records) on the main stream.
+    copy_in.wait_stream(main)
+    pts = points.to(device, non_blocking=True).reshape(num_points, -1)
+    plans = {}
+    for n in sorted(set(sizes), reverse=True):
+      plans[n] = _get_plan((ttype, tuple(reversed(grid_shape)), sign, n, _op_tol(tol), dcode, dev_index), opt_kwargs)
+      plans[n].set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
     out_ready = [torch.cuda.Event() for _ in range(2)]
     out_free = [torch.cuda.Event() for _ in range(2)]
-    copy_in.wait_stream(main)
-    nchunks = (T + chunk - 1) // chunk
-    for k in range(nchunks):
-      b0 = k * chunk
-      n = min(chunk, T - b0)
+    b0 = 0
+    for k, n in enumerate(sizes):
       s = k & 1
       with torch.cuda.stream(copy_in):
         if k >= 2:
@@ -296,7 +299,7 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
       main.wait_event(in_ready[s])
       if k >= 2:
         main.wait_event(out_free[s])
-      pl = plan if n == chunk else plan_rem
+      pl = plans[n]
       if ttype == 1:
         pl.execute(d_in[s].data_ptr(), d_out[s].data_ptr(), main.cuda_stream)
       else:
@@ -307,6 +310,7 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
         copy_out.wait_event(out_ready[s])
         out[b0:b0 + n].copy_(d_out[s][:n], non_blocking=True)
         out_free[s].record(copy_out)
+      b0 += n
     main.wait_stream(copy_out)
     main.synchronize()
   return out.reshape(target_shape)
