@@ -1,26 +1,22 @@
-"""Scratch: run one plan configuration a few times (for ncu captures)."""
+"""Scratch: run one plan configuration a few times with the engine's default kernels (for ncu
+captures). Usage: prof_one.py cfg{1,2,3,4} <transform type 1|2> [coils]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tensorflow_nufft_b200 import _lib
 from tests import helpers as H
-cfg, meth = sys.argv[1], int(sys.argv[2])
-bins = tuple(int(x) for x in sys.argv[3].split("x")) if len(sys.argv) > 3 else None
-ttype = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+cfg, ttype = sys.argv[1], int(sys.argv[2])
 if cfg == "cfg2":
-  grid, pts, T = (512, 512), H.spiral_points(32, 62500), 8
+  grid, pts, T = (512, 512), H.spiral_points(32, 62500), 32
 elif cfg == "cfg3":
   grid, pts, T = (128, 128, 128), H.uniform_points(8000000, 3, 3), 1
 elif cfg == "cfg4":
   grid, pts, T = (256, 256, 256), H.stack_of_stars_points(125, 125, 256), 2
 else:
   grid, pts, T = (256, 256), H.radial_points(200, 500), 1
+if len(sys.argv) > 3: T = int(sys.argv[3])
 M = pts.shape[0]; N = int(np.prod(grid))
-kw = dict(spread_method=meth, interp_method=min(meth, 2))
-if bins: kw["bin_dims"] = bins
-if os.environ.get("NC"): kw["coils_per_cta"] = int(os.environ["NC"])
-if os.environ.get("TCOILS"): T = int(os.environ["TCOILS"])
-plan = _lib.Plan(ttype, grid[::-1], -1, T, 1e-6, 0, device=0, **kw)
+plan = _lib.Plan(ttype, grid[::-1], -1, T, 1e-6, 0, device=0)
 dp = torch.from_numpy(pts).cuda()
 c = torch.from_numpy(H.random_complex((T, M), 1)).cuda()
 f = torch.from_numpy(H.random_complex((T, N), 2)).cuda()

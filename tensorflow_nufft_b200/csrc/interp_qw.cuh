@@ -25,23 +25,57 @@ namespace b200 {
 constexpr int kQwHaloX = 10;   // tile x extent = bin_x + 10 (stencil reach 8 + 2 pad cells for the pitch)
 
 template <int RANK>
-inline size_t interp_qw_smem_bytes(const int* bin) {
+inline size_t interp_qw_smem_bytes(const int* bin, int coils = 1) {
   const size_t ncell = static_cast<size_t>(bin[0] + kQwHaloX) * (bin[1] + 8) * (RANK > 2 ? bin[2] + 8 : 1);
-  return ((ncell * sizeof(float2) + 127) & ~static_cast<size_t>(127)) + 16;
+  return ((coils * ncell * sizeof(float2) + 127) & ~static_cast<size_t>(127)) + 16;
 }
 
-// Gathers the points [0, np) of one subproblem from `tile4` (origin ox, oy, oz; pitch TX cells).
-// Groups of 4 points are dealt round-robin to the `nwarps` warps. Records are read from global
-// memory (sorted order, base index p0).
-template <int NS, int RANK, typename WaitTile>
+// Transposing reduction over the 8 lanes of a quarter warp: N values per lane in, ONE value per
+// lane out (N + ... shuffles instead of 3 N): at each xor step a lane keeps one half of its values
+// and hands the other half to its partner. Afterwards lane row r holds the sum of value index
+// r / (8 / N) (rows that share an index hold copies).
+template <int N>
+__device__ __forceinline__ float qw_reduce(float (&v)[N], int lane) {
+  static_assert(N == 2 || N == 4 || N == 8, "2, 4 or 8 values");
+  int n = N;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    if (n > 1) {
+      const bool up = (lane & o) != 0;
+      const int h = n / 2;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < h) {
+          const float keep = up ? v[i + h] : v[i];
+          const float send = up ? v[i] : v[i + h];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+  return v[0];
+}
+
+// Gathers the points [0, np) of one subproblem from NC coil tiles (`tile4`, tile k at offset
+// k * ncell / 2 float4; origin ox, oy, oz; pitch TX cells). Groups of 4 points are dealt
+// round-robin to the `nwarps` warps. Records are read from global memory (sorted order, base
+// index p0) ONCE for the NC coils. Output: ct[k * M + id].
+template <int NS, int RANK, int NC, typename WaitTile>
 __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __restrict__ tile4, int TX, int TY, int TZ, int ox, int oy, int oz,
                                           int p0, int np, int warp, int nwarps, int lane,
                                           const int* __restrict__ idx, const int4* __restrict__ start,
-                                          const float4* __restrict__ wrec4, float2* __restrict__ ct) {
+                                          const float4* __restrict__ wrec4, float2* __restrict__ ct, int64_t M) {
   constexpr int C4 = 2 * RANK;
+  constexpr int NV = 2 * NC;            // values per lane: (re, im) per coil
+  constexpr int NR = NV > 8 ? 8 : NV;   // values per reduction (NC = 8: two reductions of 8)
+  constexpr int DUP = 8 / NR;           // rows of a quarter that end up with the same value
   const int pt = lane >> 3;
   const int row = lane & 7;
   const int zstride4 = TY * TX / 2;
+  const int tile_f4 = zstride4 * TZ;
   const int ngrp = (np + 3) >> 2;
 
   float4 wxa, wxb, wza, wzb;
@@ -74,46 +108,59 @@ __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __
     fetch(grp + nwarps);
 
     const bool valid = 4 * grp + pt < np;
-    float re = 0.f, im = 0.f;
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.f;
     const int rx = st_c.x - ox, ry = st_c.y - oy, rz = RANK > 2 ? st_c.z - oz : 0;
     // Memory safety for coordinates outside the declared points_range (see interp.cuh).
     const bool fits = rx >= 0 && rx + 8 <= TX && ry >= 0 && ry + NS <= TY && (RANK < 3 || (rz >= 0 && rz + NS <= TZ));
     if (valid && fits && row < NS) {
       const float4* ptr = tile4 + (((rz * TY + ry + row) * TX + rx) >> 1);
-      if (RANK == 2) {
-        const float4 v0 = ptr[0], v1 = ptr[1], v2 = ptr[2], v3 = ptr[3];
-        re = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
-        im = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
-      } else {
-        const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
-        for (int dz = 0; dz < NS; ++dz) {
-          const float4* pz = ptr + dz * zstride4;
-          const float4 v0 = pz[0], v1 = pz[1], v2 = pz[2], v3 = pz[3];
-          const float pr = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
-          const float pi = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
-          re += wz[dz] * pr;
-          im += wz[dz] * pi;
+      for (int k = 0; k < NC; ++k) {
+        const float4* pk = ptr + k * tile_f4;
+        float re = 0.f, im = 0.f;
+        if (RANK == 2) {
+          const float4 v0 = pk[0], v1 = pk[1], v2 = pk[2], v3 = pk[3];
+          re = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
+          im = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
+        } else {
+          const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+          for (int dz = 0; dz < NS; ++dz) {
+            const float4* pz = pk + dz * zstride4;
+            const float4 v0 = pz[0], v1 = pz[1], v2 = pz[2], v3 = pz[3];
+            const float pr = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
+            const float pi = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
+            re += wz[dz] * pr;
+            im += wz[dz] * pi;
+          }
         }
+        v[2 * k] = re * wy_c;
+        v[2 * k + 1] = im * wy_c;
       }
-      re *= wy_c;
-      im *= wy_c;
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      re += __shfl_xor_sync(0xffffffffu, re, o);
-      im += __shfl_xor_sync(0xffffffffu, im, o);
+    for (int h = 0; h < NV / NR; ++h) {
+      float part[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) part[i] = v[h * NR + i];
+      const float sum = qw_reduce<NR>(part, lane);
+      // lane row r holds value index h * NR + r / DUP = 2 * coil + (0: re, 1: im)
+      const int vi = h * NR + row / DUP;
+      if (valid && (row % DUP) == 0)
+        reinterpret_cast<float*>(ct + static_cast<int64_t>(vi >> 1) * M + id_c)[vi & 1] = sum;
     }
-    if (valid && row == 0) ct[id_c] = make_float2(re, im);
   }
 }
 
-// One CTA (WARPS warps) per (subproblem, transform); tile staged by ONE TMA box copy (interior) or
+// One CTA (WARPS warps) per (subproblem, group of NC transforms); the NC coil tiles are staged by ONE TMA
+// box copy (interior; the box spans NC transforms) or
 // wrapped 16-byte cp.async copies (tiles that straddle the periodic boundary); the other resident
 // CTAs of the SM hide the tile latency. (A persistent grid-stride variant and a two-stage tile ring
 // were measured slower on every BASELINE config: static striding loses the hardware scheduler's
 // load balancing between heavy and light subproblems.)
-template <int NS, int RANK, int WARPS>
+template <int NS, int RANK, int NC, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
@@ -124,7 +171,7 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = blockIdx.y;
+  const int t = blockIdx.y * NC;   // first transform of this CTA's group
   const int4 sd = sub_desc[s];
   const int b = sd.x, p0 = sd.y, np = sd.z;
 
@@ -137,7 +184,7 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   const int ncell = TX * TY * TZ;
   const int TXH = TX / 2;
   float4* tile4 = smem4;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem4) + ((static_cast<size_t>(ncell) * sizeof(float2) + 127) & ~static_cast<size_t>(127)));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem4) + ((static_cast<size_t>(NC) * ncell * sizeof(float2) + 127) & ~static_cast<size_t>(127)));
 
   const float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
   const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
@@ -146,7 +193,7 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(bar, static_cast<uint32_t>(ncell * sizeof(float2)));
+      mbar_expect_tx(bar, static_cast<uint32_t>(NC * ncell * sizeof(float2)));
       if (RANK == 2) tma_load_3d(tile4, &tmap, bar, 2 * ox, oy, t);
       else tma_load_4d(tile4, &tmap, bar, 2 * ox, oy, oz, t);
     }
@@ -158,7 +205,9 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
       const int gx = mod_idx(ox + 2 * ix, g.nf[0]);
       const int gy = mod_idx(oy + iy, g.nf[1]);
       const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
-      __pipeline_memcpy_async(&tile4[i], fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx, 16);
+      const float2* src = fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) __pipeline_memcpy_async(&tile4[k * (ncell / 2) + i], src + k * g.nftot, 16);
     }
     __pipeline_commit();
   }
@@ -170,8 +219,8 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
       __syncthreads();
     }
   };
-  qw_gather<NS, RANK>(wait_tile, tile4, TX, TY, TZ, ox, oy, oz, p0, np, warp, WARPS, lane, idx, start, wrec4,
-                      c + static_cast<int64_t>(t) * M);
+  qw_gather<NS, RANK, NC>(wait_tile, tile4, TX, TY, TZ, ox, oy, oz, p0, np, warp, WARPS, lane, idx, start, wrec4,
+                          c + static_cast<int64_t>(t) * M, M);
 }
 
 }  // namespace b200

@@ -80,6 +80,7 @@ struct b200nufft_plan {
   const void* tmap_ptr = nullptr;
   int tmap_batch = 0;
   int tmap_halo = 0;
+  int tmap_coils = 0;
   bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
@@ -256,8 +257,8 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8) {
-  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == halo_x) return true;
+bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8, int box_coils = 1) {
+  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == halo_x && p->tmap_coils == box_coils) return true;
   static EncodeTiledFn encode = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -284,7 +285,7 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
     row *= p->nf[d];
   }
   dims[rank] = ntr;
-  box[rank] = 1;
+  box[rank] = box_coils;
   strides[rank - 1] = static_cast<cuuint64_t>(p->nftot) * 8;
   for (int d = 0; d <= rank; ++d) if (box[d] > 256) return false;
   CUresult r = encode(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank + 1, const_cast<void*>(grid), dims, strides, box,
@@ -294,6 +295,7 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
   p->tmap_ptr = grid;
   p->tmap_batch = ntr;
   p->tmap_halo = halo_x;
+  p->tmap_coils = box_coils;
   p->tma_ok = true;
   return true;
 }
@@ -324,15 +326,15 @@ cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, flo
 
 constexpr int kQwWarps = 4;
 
-template <int RANK>
+template <int RANK, int NC>
 cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, kQwHaloX)) ? 1 : 0;
-  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
-  const size_t smem = interp_qw_smem_bytes<RANK>(p->bin);
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, kQwHaloX, NC)) ? 1 : 0;
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
+  const size_t smem = interp_qw_smem_bytes<RANK>(p->bin, NC);
 #define QW_CASE(NS)                                                                              \
   case NS: {                                                                                     \
-    auto k = interp_qw_f32_kernel<NS, RANK, kQwWarps>;                                           \
+    auto k = interp_qw_f32_kernel<NS, RANK, NC, kQwWarps>;                                       \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kQwWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),        \
@@ -398,9 +400,18 @@ template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
   if (p->interp_method >= 3) {
-    cudaError_t e = p->rank == 2
-        ? launch_interp_qw<2>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st)
-        : launch_interp_qw<3>(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    const float2* ff = static_cast<const float2*>(fw);
+    float2* cc = static_cast<float2*>(c);
+    // 2D: NC coils per CTA share the record loads (the L1 data pipe is the bound); 3D: one coil
+    // (cfg2 mirrored to type 2, 32 coils: 1.20 ms at 8 coils per CTA, 1.29 at 4, 2.04 at 1)
+    const int nc_opt = p->opts.reserved[1];
+    const int nc = nc_opt > 0 ? nc_opt : 8;
+    cudaError_t e;
+    if (p->rank == 3) e = launch_interp_qw<3, 1>(p, ntr, ff, cc, st);
+    else if (nc >= 8 && ntr % 8 == 0) e = launch_interp_qw<2, 8>(p, ntr, ff, cc, st);
+    else if (nc >= 4 && ntr % 4 == 0) e = launch_interp_qw<2, 4>(p, ntr, ff, cc, st);
+    else if (nc >= 2 && ntr % 2 == 0) e = launch_interp_qw<2, 2>(p, ntr, ff, cc, st);
+    else e = launch_interp_qw<2, 1>(p, ntr, ff, cc, st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp qw launch: %s", cudaGetErrorString(e));
   } else if (p->interp_method == 2) {
     cudaError_t e = p->rank == 2
@@ -724,7 +735,7 @@ int create_impl(b200nufft_plan* p) {
     size_t need = 0;
     if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
-    if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin) : interp_qw_smem_bytes<3>(p->bin));
+    if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin, 8) : interp_qw_smem_bytes<3>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)

@@ -228,14 +228,18 @@ __device__ __forceinline__ F es_eval_fast(F x, F beta, F c, F half_width) {
 }
 template <>
 __device__ __forceinline__ float es_eval_fast<float>(float x, float beta, float c, float half_width) {
-  const float t = mul_rn(mul_rn(c, x), x);
+  // Outside the support the value is 0 whatever the exponent: evaluate it at t = 0 there so that
+  // the (slow, double precision) near-edge path of es_exponent_ff is taken only by taps that are
+  // inside the support AND within 1e-5 of its edge, not by every zero-padded tap.
+  const bool outside = fabsf(x) >= half_width;
+  const float t = outside ? 0.f : mul_rn(mul_rn(c, x), x);
   const float e = es_exponent_ff(t, beta);
 #ifdef B200NUFFT_FAST_EXP
   const float k = expf(e);
 #else
   const float k = static_cast<float>(exp(static_cast<double>(e)));
 #endif
-  return (fabsf(x) >= half_width) ? 0.f : k;
+  return outside ? 0.f : k;
 }
 
 // Per-point stencil record, in sorted order j (point id idx[j]):
@@ -301,8 +305,9 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
     F w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int t = k - shift;
-      w[k] = (t >= 0 && t < ns) ? es_eval_fast<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width) : F(0);
+      // Taps t < 0 and t >= ns lie outside the support (x1 in [-ns/2, -ns/2 + 1)) and evaluate
+      // to exactly 0: no per-lane condition, no divergence between lanes with different shifts.
+      w[k] = es_eval_fast<F>(add_rn(x1, static_cast<F>(k - shift)), beta, c, half_width);
     }
     F* out = wrec + g * 8;
 #pragma unroll
