@@ -496,8 +496,8 @@ int execute_impl(b200nufft_plan* p, void* c_, void* f_, cudaStream_t st) {
       if (prof) cudaEventRecord(ev[3], st);
     } else {
       if (prof) cudaEventRecord(ev[0], st);
-      dim3 grid(static_cast<unsigned>(p->nftot / p->nf[0]), ntr);
-      amplify_kernel<F><<<grid, std::min<int>(256, std::max<int>(32, (p->nf[0] + 31) / 32 * 32)), 0, st>>>(mg, p1, p2, p3, fb, fw);
+      dim3 grid(static_cast<unsigned>((p->nftot / p->nf[0] + kAmplifyRowsPerCta - 1) / kAmplifyRowsPerCta), ntr);
+      amplify_kernel<F><<<grid, 32 * kAmplifyRowsPerCta, 0, st>>>(mg, p1, p2, p3, fb, fw);
       LAUNCH_OK(p);
       p->launches++;
       if (prof) cudaEventRecord(ev[1], st);
