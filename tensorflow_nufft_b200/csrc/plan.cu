@@ -96,7 +96,7 @@ struct b200nufft_plan {
 
   int64_t M = 0;
   bool points_set = false;
-  DevBuf folded[3], keys0, keys1, vals0, vals1, hist, start, wrec;
+  DevBuf folded, keys0, keys1, vals0, vals1, hist, start, wrec;
   DevBuf bin_sizes, bin_start, num_sub, sub_start, sub_desc, misc;  // misc: scan tmp[1024] + sub_total + range flag
   int* idx = nullptr;      // points at vals0 or vals1
   int64_t sub_bound = 0;
@@ -529,7 +529,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     return B200NUFFT_OK;
   }
   const int rank = p->rank;
-  for (int d = 0; d < rank; ++d) CUDA_OK(p, p->folded[d].reserve(sizeof(F) * M));
+  CUDA_OK(p, p->folded.reserve(sizeof(F) * 4 * M));
   CUDA_OK(p, p->keys0.reserve(sizeof(uint32_t) * M));
   CUDA_OK(p, p->keys1.reserve(sizeof(uint32_t) * M));
   CUDA_OK(p, p->vals0.reserve(sizeof(int) * M));
@@ -556,8 +556,8 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   const int check = p->opts.check_points_range && p->opts.points_range != B200NUFFT_RANGE_INFINITE;
   fold_key_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
       M, layout, static_cast<const F*>(x), static_cast<const F*>(y), static_cast<const F*>(z),
-      p->opts.points_range, check, lo, hi, bg, static_cast<F>(p->kp.half_width), p->folded[0].as<F>(), p->folded[1].as<F>(),
-      p->folded[2].as<F>(), p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
+      p->opts.points_range, check, lo, hi, bg, static_cast<F>(p->kp.half_width), p->folded.as<F>(),
+      p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
       p->range_flag());
   LAUNCH_OK(p);
   p->launches++;
@@ -610,15 +610,15 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     const F beta = static_cast<F>(p->kp.beta), cc = static_cast<F>(p->kp.c), hw = static_cast<F>(p->kp.half_width);
     if (rank == 2)
       stencil_record8_kernel<F, 2><<<grid_for(M * 2, 256, 16), 256, 0, st>>>(
-          M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
+          M, p->idx, p->folded.as<F>(), p->kp.ns, beta, cc, hw,
           align, p->start.as<int>(), p->wrec.as<F>());
     else
       stencil_record8_kernel<F, 3><<<grid_for(M * 3, 256, 16), 256, 0, st>>>(
-          M, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns, beta, cc, hw,
+          M, p->idx, p->folded.as<F>(), p->kp.ns, beta, cc, hw,
           align_x, p->start.as<int>(), p->wrec.as<F>());
   } else {
     stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
-        M, rank, p->idx, p->folded[0].as<F>(), p->folded[1].as<F>(), p->folded[2].as<F>(), p->kp.ns,
+        M, rank, p->idx, p->folded.as<F>(), p->kp.ns,
         static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
         p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
   }
@@ -836,7 +836,8 @@ void b200nufft_plan_destroy(b200nufft_plan* p) {
   if (p->has_fft) cufftDestroy(p->fft);
   if (p->has_fft_rem) cufftDestroy(p->fft_rem);
   p->fine.release();
-  for (int d = 0; d < 3; ++d) { p->fser[d].release(); p->folded[d].release(); }
+  for (int d = 0; d < 3; ++d) p->fser[d].release();
+  p->folded.release();
   p->keys0.release(); p->keys1.release(); p->vals0.release(); p->vals1.release(); p->hist.release();
   p->start.release(); p->wrec.release(); p->bin_sizes.release(); p->bin_start.release();
   p->num_sub.release(); p->sub_start.release(); p->sub_desc.release(); p->misc.release();

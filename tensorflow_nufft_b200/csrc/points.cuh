@@ -41,6 +41,14 @@ __device__ __forceinline__ F fold_rescale(F x, int range, int nf) {
   return mul_rn(mul_rn(s, MathConst<F>::inv_two_pi), static_cast<F>(nf));
 }
 
+__device__ __forceinline__ void store_coords(float* dst, float x, float y, float z) {
+  *reinterpret_cast<float4*>(dst) = make_float4(x, y, z, 0.f);
+}
+__device__ __forceinline__ void store_coords(double* dst, double x, double y, double z) {
+  reinterpret_cast<double2*>(dst)[0] = make_double2(x, y);
+  reinterpret_cast<double2*>(dst)[1] = make_double2(z, 0.0);
+}
+
 struct BinGeom {
   int rank;
   int nf[3];
@@ -80,7 +88,7 @@ template <typename F>
 __global__ void __launch_bounds__(256)
 fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __restrict__ p1,
                 const F* __restrict__ p2, int range, int check, F lo, F hi, BinGeom g, F half_width,
-                F* __restrict__ f0, F* __restrict__ f1, F* __restrict__ f2,
+                F* __restrict__ folded /* [M][4]: x, y, z, 0 */,
                 uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes,
                 int* __restrict__ range_flag) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -120,9 +128,9 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
       wy = wy < 0 ? 0 : (wy >= g.WY ? g.WY - 1 : wy);
       key = key * (g.WX * g.WY) + wy * g.WX + wx;
     }
-    f0[i] = x[0];
-    if (g.rank > 1) f1[i] = x[1];
-    if (g.rank > 2) f2[i] = x[2];
+    // one 16 / 32-byte record per point: the record kernel gathers a point's coordinates through
+    // the sort permutation, and three separate arrays cost three 32-byte sectors per point
+    store_coords(folded + 4 * i, x[0], x[1], x[2]);
     keys[i] = static_cast<uint32_t>(key);
     vals[i] = static_cast<int>(i);
     // Warp-aggregated histogram: one atomic per distinct bin per warp (hot bins, e.g. the
@@ -252,8 +260,8 @@ __device__ __forceinline__ float es_eval_fast<float>(float x, float beta, float 
 // precision sqrt/exp work is spread evenly over the lanes.
 template <typename F>
 __global__ void __launch_bounds__(288)
-stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F* __restrict__ f0,
-                      const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
+stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F* __restrict__ folded /* [M][4] */,
+                      int ns, F beta, F c, F half_width,
                       int align_x, int R, int PX, int PY, int4* __restrict__ start, F* __restrict__ wrec) {
   // block = (R, points per block): k = threadIdx.x, no integer division anywhere.
   const int k = threadIdx.x;
@@ -263,7 +271,7 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
     const int d = k < PX ? 0 : (k < PX + PY ? 1 : 2);
     const int tap = d == 0 ? k : (d == 1 ? k - PX : k - PX - PY);
     const int i = idx[j];
-    const F x = d == 0 ? f0[i] : (d == 1 ? f1[i] : f2[i]);
+    const F x = folded[4 * static_cast<int64_t>(i) + d];
     const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
     const F x1 = sub_rn(static_cast<F>(i1), x);
     const int shift = (d == 0 && align_x) ? (i1 & 1) : 0;
@@ -273,8 +281,8 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
     wrec[g] = wv;
     if (k == 0) {
       int4 st = make_int4(i1 - shift, 0, 0, shift);
-      if (rank > 1) st.y = static_cast<int>(ceil(sub_rn(f1[i], half_width)));
-      if (rank > 2) st.z = static_cast<int>(ceil(sub_rn(f2[i], half_width)));
+      if (rank > 1) st.y = static_cast<int>(ceil(sub_rn(folded[4 * static_cast<int64_t>(i) + 1], half_width)));
+      if (rank > 2) st.z = static_cast<int>(ceil(sub_rn(folded[4 * static_cast<int64_t>(i) + 2], half_width)));
       start[j] = st;
     }
   }
@@ -288,8 +296,8 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
 // spreader's row alignment.
 template <typename F, int RANK>
 __global__ void __launch_bounds__(256)
-stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restrict__ f0,
-                       const F* __restrict__ f1, const F* __restrict__ f2, int ns, F beta, F c, F half_width,
+stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restrict__ folded /* [M][4] */,
+                       int ns, F beta, F c, F half_width,
                        int align, int* __restrict__ start /* int4 per point */, F* __restrict__ wrec) {
   const int64_t total = M * RANK;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -297,8 +305,7 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
     const int64_t j = g / RANK;
     const int d = static_cast<int>(g - j * RANK);
     const int i = idx[j];
-    const F* fd = d == 0 ? f0 : (d == 1 ? f1 : f2);
-    const F x = fd[i];
+    const F x = folded[4 * static_cast<int64_t>(i) + d];
     const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
     const F x1 = sub_rn(static_cast<F>(i1), x);
     const int shift = ((align >> d) & 1) ? (i1 & 1) : 0;
