@@ -22,6 +22,7 @@
 #include "host_params.h"
 #include "interp.cuh"
 #include "interp_qw.cuh"
+#include "rowlane_f64.cuh"
 #include "points.cuh"
 #include "scan_sort.cuh"
 #include "spread.cuh"
@@ -81,6 +82,9 @@ struct b200nufft_plan {
   int tmap_batch = 0;
   int tmap_halo = 0;
   int tmap_coils = 0;
+  int tmap_box_y = 0;
+  RowLaneGeom rl{};        // complex128 2D tile kernels
+  int rl_pxt = 0, rl_lp = 0;
   bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
@@ -257,8 +261,13 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8, int box_coils = 1) {
-  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == halo_x && p->tmap_coils == box_coils) return true;
+bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8, int box_coils = 1,
+                       int box_x_cells = 0, int box_y = 0) {
+  // box_x_cells / box_y > 0: explicit box (row-lane complex128 tiles); else bin + halo (float tiles)
+  const int bxc = box_x_cells > 0 ? box_x_cells : p->bin[0] + halo_x;
+  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == bxc && p->tmap_coils == box_coils &&
+      p->tmap_box_y == box_y)
+    return true;
   static EncodeTiledFn encode = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -272,30 +281,33 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
   p->tma_ok = false;
   if (!encode) return false;
   const int rank = p->rank;
+  const size_t real_bytes = p->is_double ? 8 : 4;
   cuuint64_t dims[4];
   cuuint64_t strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   dims[0] = 2ull * p->nf[0];
-  box[0] = 2u * (p->bin[0] + halo_x);
-  cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 8;
+  box[0] = 2u * bxc;
+  cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 2 * real_bytes;
   for (int d = 1; d < rank; ++d) {
     dims[d] = p->nf[d];
-    box[d] = p->bin[d] + 8;
+    box[d] = (d == 1 && box_y > 0) ? box_y : p->bin[d] + 8;
     strides[d - 1] = row;
     row *= p->nf[d];
   }
   dims[rank] = ntr;
   box[rank] = box_coils;
-  strides[rank - 1] = static_cast<cuuint64_t>(p->nftot) * 8;
+  strides[rank - 1] = static_cast<cuuint64_t>(p->nftot) * 2 * real_bytes;
   for (int d = 0; d <= rank; ++d) if (box[d] > 256) return false;
-  CUresult r = encode(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank + 1, const_cast<void*>(grid), dims, strides, box,
+  CUresult r = encode(&p->tmap, p->is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      rank + 1, const_cast<void*>(grid), dims, strides, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   p->tmap_ptr = grid;
   p->tmap_batch = ntr;
-  p->tmap_halo = halo_x;
+  p->tmap_halo = bxc;
   p->tmap_coils = box_coils;
+  p->tmap_box_y = box_y;
   p->tma_ok = true;
   return true;
 }
@@ -350,10 +362,50 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
   return cudaGetLastError();
 }
 
+cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const double2* fw, double2* c, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, 0, 1, p->rl.TX, p->rl.TY)) ? 1 : 0;
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = rowlane_smem_bytes(p->rl);
+#define RL_CASE(PXT, LP)                                                                         \
+  if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
+    auto k = interp_rowlane_f64_kernel<PXT, LP, 4>;                                              \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, 128, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,   \
+                               p->start.as<int4>(), p->wrec.as<double>(), fw, c, p->tmap, use_tma); \
+    return cudaGetLastError();                                                                   \
+  }
+  RL_CASE(8, 8) RL_CASE(12, 8) RL_CASE(12, 16) RL_CASE(16, 16)
+#undef RL_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const double2* c, double2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
+  const size_t smem = rowlane_smem_bytes(p->rl);
+#define RL_CASE(PXT, LP)                                                                         \
+  if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
+    auto k = spread_rowlane_f64_kernel<PXT, LP>;                                                 \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<grid, 32, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,    \
+                              p->start.as<int4>(), p->wrec.as<double>(), c, fw);                 \
+    return cudaGetLastError();                                                                   \
+  }
+  RL_CASE(8, 8) RL_CASE(12, 8) RL_CASE(12, 16) RL_CASE(16, 16)
+#undef RL_CASE
+  return cudaErrorInvalidValue;
+}
+
 template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->spread_method == 4) {
+  if (p->spread_method == 5) {
+    cudaError_t e = launch_spread_rowlane(p, ntr, static_cast<const double2*>(c), static_cast<double2*>(fw), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread rowlane launch: %s", cudaGetErrorString(e));
+  } else if (p->spread_method == 4) {
     cudaError_t e;
     const float2* cc = static_cast<const float2*>(c);
     float2* ff = static_cast<float2*>(fw);
@@ -399,7 +451,10 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
 template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
-  if (p->interp_method >= 3) {
+  if (p->interp_method == 5) {
+    cudaError_t e = launch_interp_rowlane(p, ntr, static_cast<const double2*>(fw), static_cast<double2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp rowlane launch: %s", cudaGetErrorString(e));
+  } else if (p->interp_method >= 3) {
     const float2* ff = static_cast<const float2*>(fw);
     float2* cc = static_cast<float2*>(c);
     // 2D: NC coils per CTA share the record loads (the L1 data pipe is the bound); 3D: one coil
@@ -690,6 +745,14 @@ int create_impl(b200nufft_plan* p) {
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
+  // complex128 in 2D: row-lane tile kernels (rowlane_f64.cuh) unless the generic kernels are asked for
+  const bool rl_ok = p->is_double && p->rank == 2 && ns <= 15;
+  if (rl_ok) {
+    if (p->opts.spread_method != 1) p->spread_method = 5;
+    if (p->opts.interp_method != 1) p->interp_method = 5;
+    p->rl_pxt = p->PX;
+    p->rl_lp = p->PY <= 8 ? 8 : 16;
+  }
   // ws2 is 2D, type-1 NUFFT plans only (its records are not usable by the other kernels)
   if (p->spread_method == 4 && (p->rank != 2 || p->type != 1 || p->opts.spread_only)) p->spread_method = 3;
   const bool ws_any = p->spread_method == 3 || p->spread_method == 4;
@@ -701,6 +764,7 @@ int create_impl(b200nufft_plan* p) {
     def_bin[0] = (p->type == 1 && ws_any) ? 16 : 32;
     def_bin[1] = (p->type == 1 && ws_any) ? 8 : 32;
     if (p->type == 2 && p->interp_method == 3) { def_bin[0] = 16; def_bin[1] = 16; }   // cfg2-type2 0.559 vs 0.565 ms, cfg1 12 vs 14 us
+    if (rl_ok) { def_bin[0] = 16; def_bin[1] = 16; }
   }
   else {
     def_bin[0] = 16;
@@ -729,7 +793,14 @@ int create_impl(b200nufft_plan* p) {
     p->spread_method = 2;
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
-  if (uses_tile || uses_tile_i) {
+  if (rl_ok && (p->spread_method == 5 || p->interp_method == 5)) {
+    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX);
+    p->tile_smem = rowlane_smem_bytes(p->rl);
+    if (p->tile_smem > 227 * 1024) {   // user-chosen bins too large: fall back to the generic kernels
+      p->spread_method = 1;
+      p->interp_method = 1;
+    }
+  } else if (uses_tile || uses_tile_i) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;

@@ -165,6 +165,20 @@ CASES = [
     (2, (9, 7), 500, 5, 2, np.complex64, 1e-5, "uniform"),
     (3, (5, 6, 7), 400, 1, 1, np.complex64, 1e-4, "uniform"),
     (3, (5, 6, 7), 400, 1, 2, np.complex64, 1e-4, "uniform"),
+    # coil counts that select the 8 / 4 / 2 / 1 coils-per-CTA variants of the 2D spreader and
+    # interpolator (8 | T, 4 | T, 2 | T, odd)
+    (2, (96, 72), 30000, 4, 1, np.complex64, 1e-6, "spiral"),
+    (2, (96, 72), 30000, 4, 2, np.complex64, 1e-6, "spiral"),
+    (2, (96, 72), 30000, 6, 1, np.complex64, 1e-6, "uniform"),
+    (2, (96, 72), 30000, 6, 2, np.complex64, 1e-6, "uniform"),
+    (2, (96, 72), 30000, 8, 1, np.complex64, 1e-6, "radial"),
+    (2, (96, 72), 30000, 8, 2, np.complex64, 1e-6, "radial"),
+    (2, (80, 112), 20000, 16, 1, np.complex64, 1e-5, "uniform"),
+    (2, (80, 112), 20000, 16, 2, np.complex64, 1e-5, "uniform"),
+    (2, (80, 112), 20000, 7, 1, np.complex64, 1e-2, "uniform"),   # ns = 4 through the window kernels
+    (2, (80, 112), 20000, 7, 2, np.complex64, 1e-2, "uniform"),
+    (3, (24, 40, 32), 30000, 4, 2, np.complex64, 1e-5, "sos"),
+    (3, (24, 40, 32), 30000, 4, 1, np.complex64, 1e-5, "sos"),
 ]
 
 
@@ -172,11 +186,11 @@ def _points(kind, M, rank, rdtype, seed):
   if kind == "uniform":
     return H.uniform_points(M, rank, seed, rdtype)
   if kind == "radial":
-    return H.radial_points(200, M // 200, rdtype)
+    return H.radial_points(max(1, M // 500), min(M, 500), rdtype) if M < 100000 else H.radial_points(200, M // 200, rdtype)
   if kind == "spiral":
     return H.spiral_points(8, M // 8, 24, rdtype)
   if kind == "sos":
-    return H.stack_of_stars_points(20, 100, M // 2000, rdtype)
+    return H.stack_of_stars_points(20, 100, max(1, M // 2000), rdtype)
   raise ValueError(kind)
 
 
