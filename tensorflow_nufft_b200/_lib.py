@@ -147,6 +147,8 @@ class Plan:
         opts.reserved[1] = int(v)
       elif k == "kernel_variant":
         opts.reserved[2] = int(v)
+      elif k == "full_fft":
+        opts.reserved[4] = int(v)
       else:
         if not hasattr(opts, k):
           raise TypeError(f"unknown option {k}")

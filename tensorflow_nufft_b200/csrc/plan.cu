@@ -97,6 +97,12 @@ struct b200nufft_plan {
   cufftHandle fft = 0, fft_rem = 0;
   bool has_fft = false, has_fft_rem = false;
   int fft_rem_batch = 0;
+  // Pruned 3D FFT (3 cuFFT plans on the fine grid): the slowest axis holds modes only in its first
+  // zlo and last zhi planes (zero padding on input for type 2, cropped output for type 1), so the
+  // 2D (x, y) transforms run on those planes only and a strided 1D transform does the z axis.
+  cufftHandle fft_xy_lo = 0, fft_xy_hi = 0, fft_z = 0;
+  bool pruned_fft = false;
+  int zlo = 0, zhi = 0;
 
   int64_t M = 0;
   bool points_set = false;
@@ -484,6 +490,34 @@ int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t 
 }
 
 int do_fft(b200nufft_plan* p, int ntr, cudaStream_t st) {
+  const int dir = p->fft_sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
+  if (p->pruned_fft) {
+    const size_t cs = p->is_double ? sizeof(double2) : sizeof(float2);
+    const int64_t plane = static_cast<int64_t>(p->nf[0]) * p->nf[1];
+    auto exec = [&](cufftHandle h, char* ptr) {
+      cufftResult r = cufftSetStream(h, st);
+      if (r != CUFFT_SUCCESS) return r;
+      p->launches++;
+      return p->is_double ? cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(ptr), reinterpret_cast<cufftDoubleComplex*>(ptr), dir)
+                          : cufftExecC2C(h, reinterpret_cast<cufftComplex*>(ptr), reinterpret_cast<cufftComplex*>(ptr), dir);
+    };
+    for (int t = 0; t < ntr; ++t) {
+      char* base = p->fine.as<char>() + cs * p->nftot * t;
+      char* hi = base + cs * plane * (p->nf[2] - p->zhi);
+      cufftResult r = CUFFT_SUCCESS;
+      if (p->type == 2) {   // zero-padded input: (x, y) on the populated planes, then z everywhere
+        r = exec(p->fft_xy_lo, base);
+        if (r == CUFFT_SUCCESS && p->zhi > 0) r = exec(p->fft_xy_hi, hi);
+        if (r == CUFFT_SUCCESS) r = exec(p->fft_z, base);
+      } else {              // cropped output: z everywhere, then (x, y) on the planes that are kept
+        r = exec(p->fft_z, base);
+        if (r == CUFFT_SUCCESS) r = exec(p->fft_xy_lo, base);
+        if (r == CUFFT_SUCCESS && p->zhi > 0) r = exec(p->fft_xy_hi, hi);
+      }
+      if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftExec (pruned) failed: %d", (int)r);
+    }
+    return B200NUFFT_OK;
+  }
   cufftHandle h = p->fft;
   if (ntr != p->batch) {
     if (!p->has_fft_rem || p->fft_rem_batch != ntr) {
@@ -500,7 +534,6 @@ int do_fft(b200nufft_plan* p, int ntr, cudaStream_t st) {
   }
   cufftResult r = cufftSetStream(h, st);
   if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftSetStream failed: %d", (int)r);
-  const int dir = p->fft_sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
   if (p->is_double)
     r = cufftExecZ2Z(h, p->fine.as<cufftDoubleComplex>(), p->fine.as<cufftDoubleComplex>(), dir);
   else
@@ -827,12 +860,37 @@ int create_impl(b200nufft_plan* p) {
       CUDA_OK(p, cudaMemcpy(p->fser[d].p, p->fser_host[d].data(), sizeof(F) * nc, cudaMemcpyHostToDevice));
     }
     CUDA_OK(p, p->fine.reserve(sizeof(Cplx<F>) * p->nftot * p->batch));
-    int n[3];
-    for (int d = 0; d < p->rank; ++d) n[d] = p->nf[p->rank - 1 - d];
-    cufftResult r = cufftPlanMany(&p->fft, p->rank, n, nullptr, 1, 0, nullptr, 1, 0,
-                                  p->is_double ? CUFFT_Z2Z : CUFFT_C2C, p->batch);
-    if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftPlanMany failed: %d", (int)r);
-    p->has_fft = true;
+    const cufftType ftype = p->is_double ? CUFFT_Z2Z : CUFFT_C2C;
+    if (p->rank == 3 && p->opts.reserved[4] == 0) {
+      // modes k = -(n/2) .. (n-1)/2 live in fine planes [0, zlo) and [nf - zhi, nf)
+      p->zlo = static_cast<int>((p->n_modes[2] - 1) / 2 + 1);
+      p->zhi = static_cast<int>(p->n_modes[2] / 2);
+      if (p->zlo + p->zhi < p->nf[2]) {
+        int nxy[2] = {p->nf[1], p->nf[0]};
+        int nz[1] = {p->nf[2]};
+        const int plane = p->nf[0] * p->nf[1];
+        bool ok = cufftPlanMany(&p->fft_xy_lo, 2, nxy, nullptr, 1, 0, nullptr, 1, 0, ftype, p->zlo) == CUFFT_SUCCESS;
+        if (ok && p->zhi > 0) {
+          ok = cufftPlanMany(&p->fft_xy_hi, 2, nxy, nullptr, 1, 0, nullptr, 1, 0, ftype, p->zhi) == CUFFT_SUCCESS;
+          if (!ok) { cufftDestroy(p->fft_xy_lo); p->fft_xy_lo = 0; }
+        }
+        if (ok) {
+          ok = cufftPlanMany(&p->fft_z, 1, nz, nz, plane, 1, nz, plane, 1, ftype, plane) == CUFFT_SUCCESS;
+          if (!ok) {
+            cufftDestroy(p->fft_xy_lo); p->fft_xy_lo = 0;
+            if (p->fft_xy_hi) { cufftDestroy(p->fft_xy_hi); p->fft_xy_hi = 0; }
+          }
+        }
+        p->pruned_fft = ok;
+      }
+    }
+    if (!p->pruned_fft) {
+      int n[3];
+      for (int d = 0; d < p->rank; ++d) n[d] = p->nf[p->rank - 1 - d];
+      cufftResult r = cufftPlanMany(&p->fft, p->rank, n, nullptr, 1, 0, nullptr, 1, 0, ftype, p->batch);
+      if (r != CUFFT_SUCCESS) return set_err(p, B200NUFFT_INTERNAL, "cufftPlanMany failed: %d", (int)r);
+      p->has_fft = true;
+    }
   }
   CUDA_OK(p, p->bin_sizes.reserve(sizeof(int) * (p->nbtot + 1)));
   CUDA_OK(p, p->bin_start.reserve(sizeof(int) * (p->nbtot + 1)));
@@ -906,6 +964,9 @@ void b200nufft_plan_destroy(b200nufft_plan* p) {
   cudaSetDevice(p->device);
   if (p->has_fft) cufftDestroy(p->fft);
   if (p->has_fft_rem) cufftDestroy(p->fft_rem);
+  if (p->fft_xy_lo) cufftDestroy(p->fft_xy_lo);
+  if (p->fft_xy_hi) cufftDestroy(p->fft_xy_hi);
+  if (p->fft_z) cufftDestroy(p->fft_z);
   p->fine.release();
   for (int d = 0; d < 3; ++d) p->fser[d].release();
   p->folded.release();
