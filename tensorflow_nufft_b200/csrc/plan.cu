@@ -827,7 +827,7 @@ int create_impl(b200nufft_plan* p) {
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
   if (rl_ok && (p->spread_method == 5 || p->interp_method == 5)) {
-    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX);
+    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX, p->PY);
     p->tile_smem = rowlane_smem_bytes(p->rl);
     if (p->tile_smem > 227 * 1024) {   // user-chosen bins too large: fall back to the generic kernels
       p->spread_method = 1;

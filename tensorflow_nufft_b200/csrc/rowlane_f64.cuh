@@ -26,10 +26,10 @@ namespace b200 {
 struct RowLaneGeom {
   int TX, TY;     // tile extent in cells (TX odd)
   int hx, hy;     // tile origin = bin origin - (hx, hy)
-  int R, PX;      // record stride and wy offset, in reals
+  int R, PX, PY;  // record stride, wy offset and wy length, in reals (rows >= PY carry no weight)
 };
 
-inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, int PX) {
+inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, int PX, int PY) {
   RowLaneGeom r;
   r.hx = (ns + 1) / 2;
   r.hy = (ns + 1) / 2;
@@ -37,6 +37,7 @@ inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, 
   r.TY = bin[1] + lp + 2;
   r.R = R;
   r.PX = PX;
+  r.PY = PY;
   return r;
 }
 
@@ -110,7 +111,7 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
       const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY;
       if (fits) {
         const double* wx = wrec + j * rl.R;
-        const double wy = wx[rl.PX + row];
+        const double wy = row < rl.PY ? wx[rl.PX + row] : 0.0;
         const double2* ptr = tile_rl + (ry + row) * TX + rx;
 #pragma unroll
         for (int k = 0; k < PXT; k += 2) {
@@ -180,7 +181,7 @@ spread_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
         wxh[k] = w2.x;
         wxh[k + 1] = w2.y;
       }
-      wy = row_ok ? wx[rl.PX + row] : 0.0;
+      wy = (row_ok && row < rl.PY) ? wx[rl.PX + row] : 0.0;
       st = start[j];
       cj = ct[idx[j]];
     }

@@ -179,6 +179,24 @@ CASES = [
     (2, (80, 112), 20000, 7, 2, np.complex64, 1e-2, "uniform"),
     (3, (24, 40, 32), 30000, 4, 2, np.complex64, 1e-5, "sos"),
     (3, (24, 40, 32), 30000, 4, 1, np.complex64, 1e-5, "sos"),
+    # points exactly on the fold boundaries (+-pi, 0) mixed into a uniform set, every tile kernel
+    (2, (64, 48), 4000, 2, 1, np.complex64, 1e-6, "edges"),
+    (2, (64, 48), 4000, 2, 2, np.complex64, 1e-6, "edges"),
+    (3, (20, 24, 16), 4000, 1, 1, np.complex64, 1e-6, "edges"),
+    (3, (20, 24, 16), 4000, 1, 2, np.complex64, 1e-6, "edges"),
+    (2, (64, 48), 4000, 2, 1, np.complex128, 1e-12, "edges"),
+    (2, (64, 48), 4000, 2, 2, np.complex128, 1e-12, "edges"),
+    # complex128 row-lane kernels: every (record width, lanes per point) instantiation
+    (2, (48, 40), 10000, 3, 1, np.complex128, 1e-5, "uniform"),    # ns = 6:  PX 8,  8 lanes
+    (2, (48, 40), 10000, 3, 2, np.complex128, 1e-5, "uniform"),
+    (2, (48, 40), 10000, 1, 1, np.complex128, 1e-7, "spiral"),     # ns = 8:  PX 12, 8 lanes
+    (2, (48, 40), 10000, 1, 2, np.complex128, 1e-7, "spiral"),
+    (2, (48, 40), 10000, 2, 1, np.complex128, 1e-9, "radial"),     # ns = 10/11: PX 12, 16 lanes
+    (2, (48, 40), 10000, 2, 2, np.complex128, 1e-9, "radial"),
+    (2, (135, 77), 20000, 2, 1, np.complex128, 1e-13, "uniform"),  # ns = 15: PX 16, 16 lanes, odd grid
+    (2, (135, 77), 20000, 2, 2, np.complex128, 1e-13, "uniform"),
+    (2, (9, 7), 300, 2, 1, np.complex128, 1e-12, "uniform"),       # fine grid smaller than one tile
+    (2, (9, 7), 300, 2, 2, np.complex128, 1e-12, "uniform"),
 ]
 
 
@@ -189,6 +207,17 @@ def _points(kind, M, rank, rdtype, seed):
     return H.radial_points(max(1, M // 500), min(M, 500), rdtype) if M < 100000 else H.radial_points(200, M // 200, rdtype)
   if kind == "spiral":
     return H.spiral_points(8, M // 8, 24, rdtype)
+  if kind == "edges":
+    pts = H.uniform_points(M, rank, seed, rdtype)
+    pi = rdtype(np.pi)
+    special = [pi, -pi, rdtype(0), np.nextafter(pi, rdtype(0)), -np.nextafter(pi, rdtype(0))]
+    k = 0
+    for a in special:
+      for b in special:
+        pts[k, :] = a
+        pts[k, -1] = b
+        k += 1
+    return pts
   if kind == "sos":
     return H.stack_of_stars_points(20, 100, max(1, M // 2000), rdtype)
   raise ValueError(kind)
@@ -252,6 +281,23 @@ def test_tile_and_global_kernels_agree(rank):
     assert H.rel_l2(res[(ttype, 2)], res[(ttype, 1)]) < 5e-7
     assert H.rel_l2(res[(ttype, 3)], res[(ttype, 1)]) < 5e-7
     assert H.rel_l2(res[(ttype, 4)], res[(ttype, 1)]) < 5e-7
+
+
+@pytest.mark.parametrize("ttype", [1, 2])
+@pytest.mark.parametrize("grid", [(24, 20, 32), (9, 12, 7)])
+def test_pruned_3d_fft_matches_single_plan(ttype, grid):
+  """3D plans run the fine-grid FFT as 2D cuFFT transforms on the populated z-planes plus a strided
+  1D cuFFT along z; the result must equal the single 3D cuFFT plan to rounding."""
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  M = 20000
+  pts = H.uniform_points(M, 3, 51)
+  src = H.random_complex((2, M) if ttype == 1 else (2,) + grid, 52)
+  res = []
+  for full in (0, 1):
+    out = nufft_ops._run_op(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid, f"type_{ttype}",
+                            "backward", 1e-6, None, "nufft", engine_kwargs={"full_fft": full})
+    res.append(out.cpu().numpy())
+  assert H.rel_l2(res[0], res[1]) < 5e-7
 
 
 @pytest.mark.parametrize("rank", [2, 3])
