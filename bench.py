@@ -133,6 +133,8 @@ def run_ours(args, cfg, rank_id, world, device):
   src_np = H.random_complex(src_shape, 1000 + rank_id)
   ncores = os.cpu_count() or 1
   tfft.set_engine_defaults(num_threads_compat=ncores)
+  # a "step" includes set_points: the unchanged-points shortcut of the Python mirror stays off
+  tfft.set_points_reuse(False)
 
   # ---------------- device-resident arm: C ABI, inputs already in HBM ----------------
   d_pts = torch.from_numpy(pts_np).cuda()

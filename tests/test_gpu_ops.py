@@ -183,6 +183,36 @@ def test_interp_3d_many_points_is_deterministic():
     assert torch.equal(out, first)
 
 
+def test_point_set_reuse_skips_set_points_and_tracks_in_place_updates():
+  """an unchanged device `points` tensor is sorted once per cached plan; an in-place
+  update (version counter) or a different tensor triggers a new set_points."""
+  tfft = _tfft()
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  tfft.clear_plan_cache()
+  tfft.set_points_reuse(True)
+  src = torch.from_numpy(H.random_complex((4, 32, 40), 21)).cuda()
+  pts = torch.from_numpy(H.uniform_points(5000, 2, 22)).cuda()
+  c0, s0 = nufft_ops.STATS["set_points_calls"], nufft_ops.STATS["set_points_skipped"]
+  a = tfft.nufft(src, pts)
+  b = tfft.nufft(src, pts)
+  b2 = tfft.nufft(src, pts.detach())      # alias: same memory, same version counter
+  assert nufft_ops.STATS["set_points_calls"] - c0 == 1
+  assert nufft_ops.STATS["set_points_skipped"] - s0 == 2
+  assert torch.equal(a, b) and torch.equal(a, b2)
+  pts.mul_(0.5)                           # in place: version bump -> re-sort
+  c = tfft.nufft(src, pts)
+  assert nufft_ops.STATS["set_points_calls"] - c0 == 2
+  want = tfft.nufft(src, pts.clone())     # different tensor -> re-sort, same values
+  assert nufft_ops.STATS["set_points_calls"] - c0 == 3
+  assert torch.equal(c, want) and not torch.equal(a, c)
+  tfft.set_points_reuse(False)
+  d = tfft.nufft(src, pts)
+  d2 = tfft.nufft(src, pts)
+  assert nufft_ops.STATS["set_points_calls"] - c0 == 5
+  assert torch.equal(d, d2) and torch.equal(d, c)
+  tfft.set_points_reuse(True)
+
+
 def test_host_tensors_round_trip():
   tfft = _tfft()
   src = torch.from_numpy(H.random_complex((3, 24, 20), 11))
