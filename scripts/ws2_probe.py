@@ -19,6 +19,7 @@ def run(name, grid, pts, T, variants, reps=6, tol=1e-6):
     if "nc" in v: kw["coils_per_cta"] = v["nc"]
     if "msub" in v: kw["max_subproblem_size"] = v["msub"]
     if "var" in v: kw["kernel_variant"] = v["var"]
+    if "no_tma_flush" in v: kw["no_tma_flush"] = v["no_tma_flush"]
     plan = _lib.Plan(1, grid[::-1], 1, T, tol, 0, device=0, **kw)
     st = torch.cuda.current_stream().cuda_stream
     best = None
@@ -43,8 +44,8 @@ def run(name, grid, pts, T, variants, reps=6, tol=1e-6):
 
 if __name__ == "__main__":
   p = H.spiral_points(32, 62500)
-  V = [dict(method=3), dict(method=4), dict(method=4, nc=8), dict(method=4, var=1), dict(method=4, nc=8, var=1),
-       dict(method=4, nc=8, var=1, bins=(16, 16)), dict(method=4, nc=8, var=1, msub=512)]
+  V = [dict(method=3), dict(method=4, no_tma_flush=1), dict(method=4), dict(method=4, nc=4), dict(method=4, nc=4, no_tma_flush=1),
+       dict(method=4, bins=(16, 16)), dict(method=4, bins=(32, 8)), dict(method=4, bins=(16, 4)), dict(method=4, bins=(32, 16))]
   if len(sys.argv) > 1: V = V[:int(sys.argv[1])]
   run("cfg2-spiral-512-T32", (512, 512), p, 32, V)
   # agreement on awkward shapes: odd grid, narrow kernels, points on the fold boundaries

@@ -78,6 +78,10 @@ struct b200nufft_plan {
   int num_threads_compat = 1;
   int spread_method = 1, interp_method = 1;
   CUtensorMap tmap;        // TMA descriptor of the fine grid (type-2 tile interpolator)
+  CUtensorMap tmap_out;    // TMA descriptor of the fine grid for the spreaders' reduce-add tile flush
+  const void* tmap_out_ptr = nullptr;
+  int tmap_out_batch = 0;
+  bool tma_out_ok = false;
   const void* tmap_ptr = nullptr;
   int tmap_batch = 0;
   int tmap_halo = 0;
@@ -196,18 +200,21 @@ void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
 constexpr int kInterpWarps = 4;
 constexpr int kSpreadWarps3D = 4;   // warps sharing one 3D tile (z-plane ownership)
 
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr);
+
 template <int RANK, int WPT>
 cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = spread_tile_smem_bytes<RANK, WPT>(p->bin);
+  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
 #define SPREAD_CASE(NS)                                                                          \
   case NS: {                                                                                     \
     auto k = spread_tile_f32_kernel<NS, RANK, WPT>;                                              \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, WPT * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,     \
-                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw);           \
+                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -223,13 +230,14 @@ cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, 
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = spread_ws_smem_bytes<RANK, NC>(p->bin);
+  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
 #define WS_CASE(NS)                                                                              \
   case NS: {                                                                                     \
     auto k = spread_ws_f32_kernel<NS, RANK, TZ, NC>;                                             \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
-                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw);                 \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -245,13 +253,14 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = spread_ws_smem_bytes<2, NC>(p->bin);
+  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
 #define WS2_CASE(NS)                                                                             \
   case NS: {                                                                                     \
     auto k = spread_ws2_f32_kernel<NS, NC>;                                                          \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
-                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw);                 \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -316,6 +325,25 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
   p->tmap_box_y = box_y;
   p->tma_ok = true;
   return true;
+}
+
+// Tensor map of a spreader's output grid batch [ntr][nf2][nf1][2*nf0] float32 with a box of one
+// (bin + 8)^rank tile, for cp.reduce.async.bulk.tensor.
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
+  if (p->tma_out_ok && p->tmap_out_ptr == grid && p->tmap_out_batch == ntr) return true;
+  // reuse the encoder through a scratch plan state: encode into p->tmap, then move
+  const CUtensorMap saved = p->tmap;
+  const void* sp = p->tmap_ptr; const int sb = p->tmap_batch, sh = p->tmap_halo, sc = p->tmap_coils, sy = p->tmap_box_y;
+  const bool sok = p->tma_ok;
+  p->tma_ok = false;
+  const bool ok = ensure_tensor_map(p, grid, ntr, 8, 1);
+  if (ok) p->tmap_out = p->tmap;
+  p->tmap = saved; p->tmap_ptr = sp; p->tmap_batch = sb; p->tmap_halo = sh; p->tmap_coils = sc; p->tmap_box_y = sy;
+  p->tma_ok = sok;
+  p->tma_out_ok = ok;
+  p->tmap_out_ptr = grid;
+  p->tmap_out_batch = ntr;
+  return ok;
 }
 
 template <int RANK>

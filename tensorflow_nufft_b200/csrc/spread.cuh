@@ -13,6 +13,8 @@
 //                           conflicts (tile pitch = 8 mod 16 cells). The tile is flushed with
 //                           REDG.E.ADD.F32x4 (two complex cells per reduction), zero cells skipped.
 #pragma once
+#include <cuda.h>
+
 #include "dev_common.cuh"
 
 namespace b200 {
@@ -93,6 +95,12 @@ spread_global_kernel(int64_t M, int ntr, GridGeom g, int ns, int R, int PX, int 
 // goes on. All shared accesses in the inner loop are conflict-free 128-bit (tile pitch = 8 mod
 // 16 cells, stage record stride = 4 mod 32 words).
 // ---------------------------------------------------------------------------------------------
+// TMA reduce-add helpers (defined in interp.cuh, which includes this header)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2);
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3);
+__device__ __forceinline__ void tma_store_commit_and_wait_read();
+__device__ __forceinline__ void fence_proxy_async_smem();
+
 template <int RANK> struct StageRec {
   // spread: words [0..7] wx, [8..23] cw[r] = {Re c * wy[r], Im c * wy[r]}, [24] tile offset (cells)
   //         or -1, [25] tile z of the stencil start, [26..27] pad, [28..35] wz (3D)
@@ -107,14 +115,15 @@ __global__ void __launch_bounds__(WPT * 32)
 spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                        const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                        const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][2*RANK]*/,
-                       const float2* __restrict__ c, float2* __restrict__ fw) {
+                       const float2* __restrict__ c, float2* __restrict__ fw,
+                       const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
   constexpr int QX = (NS + 2) / 2;      // float4 lanes per stencil row: covers NS+1 cells
   static_assert(QX * NS <= 32, "stencil slab must fit one warp");
   constexpr int C4 = 2 * RANK;          // float4 chunks per weight record
   constexpr int SW = StageRec<RANK>::kWords;
   constexpr int BS = 32;                // points per batch (staged by warp 0, one point per lane)
   constexpr int NBUF = WPT > 1 ? 2 : 1;
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
@@ -259,7 +268,19 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   }
   __syncthreads();
 
-  // Flush: two complex cells per REDG.ADD.F32x4; periodic wrap; untouched (zero) pairs skipped.
+  // Flush. Interior tiles: ONE TMA reduce-add (the TMA unit reads the tile and adds it to the fine
+  // grid in L2). Tiles that straddle the periodic boundary: two complex cells per
+  // REDG.ADD.F32x4 with index wrap, untouched (zero) pairs skipped.
+  if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
+      (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]))) {
+    if (tid == 0) {
+      fence_proxy_async_smem();
+      if (RANK == 2) tma_reduce_add_3d(&tmap_out, tile4, 2 * ox, oy, t);
+      else tma_reduce_add_4d(&tmap_out, tile4, 2 * ox, oy, oz, t);
+      tma_store_commit_and_wait_read();
+    }
+    return;
+  }
   const int TXH = TX / 2;
   for (int i = tid; i < ncell / 2; i += WPT * 32) {
     const float4 v = tile4[i];

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(32)
 spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                      const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][2*RANK]*/,
-                     const float2* __restrict__ c, float2* __restrict__ fw) {
+                     const float2* __restrict__ c, float2* __restrict__ fw,
+                     const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
   constexpr int QX = (NS + 2) / 2;
   static_assert(QX * NS <= 32, "stencil slab must fit one warp");
   constexpr int C4 = 2 * RANK;
@@ -83,7 +84,7 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   using Rec = WsRec<RANK, NC>;
   constexpr int SW = Rec::kStride;
   constexpr int BS = 32;   // points per staged batch (16 was measured: no gain)
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
@@ -256,7 +257,23 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   }
   flush_run();
 
-  // Flush the tiles: two complex cells per REDG.ADD.F32x4; periodic wrap; zero pairs skipped.
+  // Flush the tiles: interior tiles by TMA reduce-add (one instruction per coil), tiles that
+  // straddle the periodic boundary with two complex cells per REDG.ADD.F32x4 (index wrap, zero
+  // pairs skipped).
+  if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
+      (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]))) {
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async_smem();
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        if (RANK == 2) tma_reduce_add_3d(&tmap_out, tile4 + k * (ncell / 2), 2 * ox, oy, t * NC + k);
+        else tma_reduce_add_4d(&tmap_out, tile4 + k * (ncell / 2), 2 * ox, oy, oz, t * NC + k);
+      }
+      tma_store_commit_and_wait_read();
+    }
+    return;
+  }
   const int TXH = TX / 2;
   for (int i = lane; i < ncell / 2; i += 32) {
     const int ix = i % TXH;

@@ -13,6 +13,7 @@
 //   * the first point of a run writes the accumulators (FMUL) instead of zeroing + FFMA.
 #pragma once
 #include "dev_common.cuh"
+#include "interp.cuh"
 #include "spread.cuh"
 #include "spread_ws.cuh"
 
@@ -23,14 +24,15 @@ __global__ void __launch_bounds__(32)
 spread_ws2_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                       const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][4]*/,
-                      const float2* __restrict__ c, float2* __restrict__ fw) {
+                      const float2* __restrict__ c, float2* __restrict__ fw,
+                      const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
   constexpr int QX = (NS + 2) / 2;
   constexpr int ROWS = NS + 1;
   static_assert(QX * ROWS <= 32, "stencil window must fit one warp");
   using Rec = WsRec<2, NC>;
   constexpr int SW = Rec::kStride;
   constexpr int BS = 32;
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) float4 smem4[];
 
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
@@ -172,7 +174,19 @@ spread_ws2_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   }
   store_run();
 
-  // Flush the tiles: two complex cells per REDG.ADD.F32x4; periodic wrap; zero pairs skipped.
+  // Flush the tiles. Interior tiles: ONE TMA reduce-add per coil (the TMA unit reads the tile and
+  // adds it to the fine grid in L2; no LSU work at all). Tiles that straddle the periodic boundary:
+  // two complex cells per REDG.ADD.F32x4 with index wrap, zero pairs skipped.
+  if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1]) {
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async_smem();   // the warp's generic-proxy tile writes -> visible to the TMA unit
+#pragma unroll
+      for (int k = 0; k < NC; ++k) tma_reduce_add_3d(&tmap_out, tile4 + k * (ncell / 2), 2 * ox, oy, t * NC + k);
+      tma_store_commit_and_wait_read();   // the tile must stay allocated until it has been read
+    }
+    return;
+  }
   const int TXH = TX / 2;
   for (int i = lane; i < ncell / 2; i += 32) {
     const int ix = i % TXH;
