@@ -833,6 +833,7 @@ int create_impl(b200nufft_plan* p) {
     def_bin[2] = (p->type == 2) ? 2 : (p->spread_method == 3 ? 8 : 2);
     if (p->type == 1 && p->spread_method == 3) def_bin[1] = 8;
     if (p->type == 2 && p->interp_method == 3) def_bin[1] = 8;   // cfg3-type2 1.18 vs 1.35 ms at 16 x 16 x 2
+    if (p->type == 1 && p->spread_method == 2) def_bin[1] = 8;   // cfg3 2.79 vs 3.01 ms at 16 x 16 x 2 (TMA flush)
   }
   p->nbtot = 1;
   for (int d = 0; d < 3; ++d) {
