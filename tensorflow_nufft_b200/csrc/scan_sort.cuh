@@ -159,43 +159,46 @@ inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stable LSD radix sort, 8-bit digits, (uint32 key, int32 value) pairs. Tile = 8 warps x 256
+// Stable LSD radix sort, 8- or 10-bit digits, (uint32 key, int32 value) pairs. Tile = 8 warps x 256
 // consecutive elements per warp; a warp walks its 256 elements in 8 rounds of 32 lanes, so the
 // (warp, round, lane) order IS the element order and ranks are stable by construction.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortWarps = 8;
 constexpr int kSortThreads = kSortWarps * 32;
 constexpr int kSortRounds = 8;
 constexpr int kSortPerWarp = 32 * kSortRounds;             // 256
 constexpr int kSortTile = kSortWarps * kSortPerWarp;       // 2048
+constexpr int kRadixBitsMax = 10;                          // 8-bit digits, or 10-bit when that saves a pass
 
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblk,
-                  int* __restrict__ hist /*[kRadix][nblk]*/) {
-  __shared__ int cnt[kRadix];
-  cnt[threadIdx.x] = 0;
+                  int* __restrict__ hist /*[1 << BITS][nblk]*/) {
+  constexpr int RADIX = 1 << BITS;
+  __shared__ int cnt[RADIX];
+  for (int d = threadIdx.x; d < RADIX; d += kSortThreads) cnt[d] = 0;
   __syncthreads();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kSortTile;
 #pragma unroll
   for (int r = 0; r < kSortTile / kSortThreads; ++r) {
     int64_t i = base + r * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & (kRadix - 1)], 1);
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & (RADIX - 1)], 1);
   }
   __syncthreads();
-  hist[static_cast<int64_t>(threadIdx.x) * nblk + blockIdx.x] = cnt[threadIdx.x];
+  for (int d = threadIdx.x; d < RADIX; d += kSortThreads) hist[static_cast<int64_t>(d) * nblk + blockIdx.x] = cnt[d];
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int64_t n,
-                     int shift, int nblk, const int* __restrict__ offs /*[kRadix][nblk] scanned*/) {
-  __shared__ int cnt[kSortWarps][kRadix];   // running per-warp digit counts
-  __shared__ int gbase[kRadix];             // global base of each digit for this block
+                     int shift, int nblk, const int* __restrict__ offs /*[1 << BITS][nblk] scanned*/) {
+  constexpr int RADIX = 1 << BITS;
+  __shared__ int cnt[kSortWarps][RADIX];   // running per-warp digit counts
+  __shared__ int gbase[RADIX];             // global base of each digit for this block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
-  gbase[threadIdx.x] = offs[static_cast<int64_t>(threadIdx.x) * nblk + blockIdx.x];
+  for (int i = threadIdx.x; i < kSortWarps * RADIX; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  for (int d = threadIdx.x; d < RADIX; d += kSortThreads) gbase[d] = offs[static_cast<int64_t>(d) * nblk + blockIdx.x];
   __syncthreads();
 
   const int64_t wbase = static_cast<int64_t>(blockIdx.x) * kSortTile + warp * kSortPerWarp;
@@ -208,8 +211,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
     const bool ok = i < n;
     key[r] = ok ? keys_in[i] : 0xffffffffu;
     val[r] = ok ? vals_in[i] : 0;
-    // Invalid lanes use digit kRadix (out of range) so they never match a real digit.
-    const unsigned dig = ok ? ((key[r] >> shift) & (kRadix - 1)) : kRadix;
+    // Invalid lanes use digit RADIX (out of range) so they never match a real digit.
+    const unsigned dig = ok ? ((key[r] >> shift) & (RADIX - 1)) : RADIX;
     const unsigned peers = __match_any_sync(0xffffffffu, dig);
     const int before = __popc(peers & ((1u << lane) - 1u));
     int prev = 0;
@@ -220,13 +223,13 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
     rank[r] = prev + before;
   }
   __syncthreads();
-  // Exclusive prefix over warps for each digit (thread d handles digit d).
-  {
+  // Exclusive prefix over warps for each digit.
+  for (int d = threadIdx.x; d < RADIX; d += kSortThreads) {
     int run = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
-      int c = cnt[w][threadIdx.x];
-      cnt[w][threadIdx.x] = run;
+      int c = cnt[w][d];
+      cnt[w][d] = run;
       run += c;
     }
   }
@@ -235,7 +238,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
   for (int r = 0; r < kSortRounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     if (i < n) {
-      const unsigned dig = (key[r] >> shift) & (kRadix - 1);
+      const unsigned dig = (key[r] >> shift) & (RADIX - 1);
       const int64_t pos = static_cast<int64_t>(gbase[dig]) + cnt[warp][dig] + rank[r];
       keys_out[pos] = key[r];
       vals_out[pos] = val[r];
@@ -253,12 +256,18 @@ inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_
   uint32_t* kin = k0; int* vin = v0; uint32_t* kout = k1; int* vout = v1;
   if (n > 0) {
     const int nblk = static_cast<int>((n + kSortTile - 1) / kSortTile);
-    const int passes = key_bits <= 0 ? 0 : (key_bits + kRadixBits - 1) / kRadixBits;
+    // 8-bit digits unless 10-bit digits save a whole pass (cfg2: 20 key bits -> 2 passes, not 3)
+    const int passes8 = key_bits <= 0 ? 0 : (key_bits + 7) / 8;
+    const int passes10 = key_bits <= 0 ? 0 : (key_bits + 9) / 10;
+    const int bits = passes10 < passes8 ? 10 : 8;
+    const int passes = bits == 10 ? passes10 : passes8;
     for (int p = 0; p < passes; ++p) {
-      const int shift = p * kRadixBits;
-      radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
-      launches += 1 + exclusive_scan_i32(hist, hist, static_cast<int64_t>(kRadix) * nblk, scan_tmp, nullptr, stream);
-      radix_scatter_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
+      const int shift = p * bits;
+      if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
+      else radix_hist_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
+      launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << bits) * nblk, scan_tmp, nullptr, stream);
+      if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
+      else radix_scatter_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
       launches += 1;
       std::swap(kin, kout);
       std::swap(vin, vout);
@@ -270,7 +279,7 @@ inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_
 }
 
 inline int64_t radix_hist_ints(int64_t n) {
-  return static_cast<int64_t>(kRadix) * ((n + kSortTile - 1) / kSortTile) + 1;
+  return (static_cast<int64_t>(1) << kRadixBitsMax) * ((n + kSortTile - 1) / kSortTile) + 1;
 }
 
 }  // namespace b200
