@@ -77,19 +77,17 @@ struct b200nufft_plan {
   int PX = 8, PY = 8, R = 8;
   int num_threads_compat = 1;
   int spread_method = 1, interp_method = 1;
-  CUtensorMap tmap;        // TMA descriptor of the fine grid (type-2 tile interpolator)
-  CUtensorMap tmap_out;    // TMA descriptor of the fine grid for the spreaders' reduce-add tile flush
-  const void* tmap_out_ptr = nullptr;
-  int tmap_out_batch = 0;
-  bool tma_out_ok = false;
-  const void* tmap_ptr = nullptr;
-  int tmap_batch = 0;
-  int tmap_halo = 0;
-  int tmap_coils = 0;
-  int tmap_box_y = 0;
+  // TMA descriptors of a grid batch with a box of one tile: `in` feeds the interpolators' tile
+  // loads, `out` the spreaders' reduce-add tile flush. Re-encoded when the pointer / box changes.
+  struct TileMap {
+    CUtensorMap map;
+    const void* ptr = nullptr;
+    int batch = 0, box_x = 0, box_y = 0, coils = 0;
+    bool ok = false;
+  };
+  TileMap tmap_in, tmap_out;
   RowLaneGeom rl{};        // complex128 2D tile kernels
   int rl_pxt = 0, rl_lp = 0;
-  bool tma_ok = false;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
   size_t tile_smem = 0;
@@ -214,7 +212,7 @@ cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, WPT * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,     \
-                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
+                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -237,7 +235,7 @@ cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, 
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
-                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -260,7 +258,7 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,           \
-                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out, use_tma); \
+                              p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -276,12 +274,12 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x = 8, int box_coils = 1,
-                       int box_x_cells = 0, int box_y = 0) {
-  // box_x_cells / box_y > 0: explicit box (row-lane complex128 tiles); else bin + halo (float tiles)
-  const int bxc = box_x_cells > 0 ? box_x_cells : p->bin[0] + halo_x;
-  if (p->tma_ok && p->tmap_ptr == grid && p->tmap_batch == ntr && p->tmap_halo == bxc && p->tmap_coils == box_coils &&
-      p->tmap_box_y == box_y)
+// Builds (or reuses) the tensor map of a grid batch [ntr][nf2][nf1][2*nf0] reals with a box of
+// box_x x box_y (x bin_z + 8) cells x box_coils transforms.
+bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const void* grid, int ntr,
+                     int box_x, int box_y, int box_coils) {
+  if (tm->ok && tm->ptr == grid && tm->batch == ntr && tm->box_x == box_x && tm->box_y == box_y &&
+      tm->coils == box_coils)
     return true;
   static EncodeTiledFn encode = nullptr;
   static bool tried = false;
@@ -293,7 +291,7 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
         qres == cudaDriverEntryPointSuccess)
       encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  p->tma_ok = false;
+  tm->ok = false;
   if (!encode) return false;
   const int rank = p->rank;
   const size_t real_bytes = p->is_double ? 8 : 4;
@@ -301,11 +299,11 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
   cuuint64_t strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   dims[0] = 2ull * p->nf[0];
-  box[0] = 2u * bxc;
+  box[0] = 2u * box_x;
   cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 2 * real_bytes;
   for (int d = 1; d < rank; ++d) {
     dims[d] = p->nf[d];
-    box[d] = (d == 1 && box_y > 0) ? box_y : p->bin[d] + 8;
+    box[d] = d == 1 ? box_y : p->bin[d] + 8;
     strides[d - 1] = row;
     row *= p->nf[d];
   }
@@ -313,43 +311,29 @@ bool ensure_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int halo_x 
   box[rank] = box_coils;
   strides[rank - 1] = static_cast<cuuint64_t>(p->nftot) * 2 * real_bytes;
   for (int d = 0; d <= rank; ++d) if (box[d] > 256) return false;
-  CUresult r = encode(&p->tmap, p->is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+  CUresult r = encode(&tm->map, p->is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                       rank + 1, const_cast<void*>(grid), dims, strides, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
-  p->tmap_ptr = grid;
-  p->tmap_batch = ntr;
-  p->tmap_halo = bxc;
-  p->tmap_coils = box_coils;
-  p->tmap_box_y = box_y;
-  p->tma_ok = true;
+  tm->ptr = grid;
+  tm->batch = ntr;
+  tm->box_x = box_x;
+  tm->box_y = box_y;
+  tm->coils = box_coils;
+  tm->ok = true;
   return true;
 }
 
-// Tensor map of a spreader's output grid batch [ntr][nf2][nf1][2*nf0] float32 with a box of one
-// (bin + 8)^rank tile, for cp.reduce.async.bulk.tensor.
+// The spreaders' output map: box = one (bin + 8)^rank tile of one transform.
 bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
-  if (p->tma_out_ok && p->tmap_out_ptr == grid && p->tmap_out_batch == ntr) return true;
-  // reuse the encoder through a scratch plan state: encode into p->tmap, then move
-  const CUtensorMap saved = p->tmap;
-  const void* sp = p->tmap_ptr; const int sb = p->tmap_batch, sh = p->tmap_halo, sc = p->tmap_coils, sy = p->tmap_box_y;
-  const bool sok = p->tma_ok;
-  p->tma_ok = false;
-  const bool ok = ensure_tensor_map(p, grid, ntr, 8, 1);
-  if (ok) p->tmap_out = p->tmap;
-  p->tmap = saved; p->tmap_ptr = sp; p->tmap_batch = sb; p->tmap_halo = sh; p->tmap_coils = sc; p->tmap_box_y = sy;
-  p->tma_ok = sok;
-  p->tma_out_ok = ok;
-  p->tmap_out_ptr = grid;
-  p->tmap_out_batch = ntr;
-  return ok;
+  return ensure_tile_map(p, &p->tmap_out, grid, ntr, p->bin[0] + 8, p->bin[1] + 8, 1);
 }
 
 template <int RANK>
 cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr)) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->bin[0] + 8, p->bin[1] + 8, 1)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = interp_tile_smem_bytes<RANK, kInterpWarps>(p->bin);
 #define INTERP_CASE(NS)                                                                          \
@@ -359,7 +343,7 @@ cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, flo
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kInterpWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),    \
                                              p->idx, p->start.as<int4>(), p->wrec.as<float4>(),  \
-                                             fw, c, p->tmap, use_tma);                           \
+                                             fw, c, p->tmap_in.map, use_tma);                           \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -375,7 +359,7 @@ constexpr int kQwWarps = 4;
 template <int RANK, int NC>
 cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, kQwHaloX, NC)) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->bin[0] + kQwHaloX, p->bin[1] + 8, NC)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = interp_qw_smem_bytes<RANK>(p->bin, NC);
 #define QW_CASE(NS)                                                                              \
@@ -385,7 +369,7 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kQwWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),        \
                                          p->idx, p->start.as<int4>(), p->wrec.as<float4>(),      \
-                                         fw, c, p->tmap, use_tma);                               \
+                                         fw, c, p->tmap_in.map, use_tma);                               \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -398,7 +382,7 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
 
 cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const double2* fw, double2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tensor_map(p, fw, ntr, 0, 1, p->rl.TX, p->rl.TY)) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->rl.TX, p->rl.TY, 1)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = rowlane_smem_bytes(p->rl);
 #define RL_CASE(PXT, LP)                                                                         \
@@ -407,7 +391,7 @@ cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const double2* fw,
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 128, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,   \
-                               p->start.as<int4>(), p->wrec.as<double>(), fw, c, p->tmap, use_tma); \
+                               p->start.as<int4>(), p->wrec.as<double>(), fw, c, p->tmap_in.map, use_tma); \
     return cudaGetLastError();                                                                   \
   }
   RL_CASE(8, 8) RL_CASE(12, 8) RL_CASE(12, 16) RL_CASE(16, 16)
