@@ -179,6 +179,11 @@ CASES = [
     (2, (80, 112), 20000, 7, 2, np.complex64, 1e-2, "uniform"),
     (3, (24, 40, 32), 30000, 4, 2, np.complex64, 1e-5, "sos"),
     (3, (24, 40, 32), 30000, 4, 1, np.complex64, 1e-5, "sos"),
+    # more transforms than one batch (32): full batches + a remainder batch with an odd coil count
+    (2, (40, 48), 6000, 37, 1, np.complex64, 1e-6, "uniform"),
+    (2, (40, 48), 6000, 37, 2, np.complex64, 1e-6, "uniform"),
+    (3, (16, 12, 20), 5000, 34, 1, np.complex64, 1e-5, "uniform"),
+    (3, (16, 12, 20), 5000, 34, 2, np.complex64, 1e-5, "uniform"),
     # points exactly on the fold boundaries (+-pi, 0) mixed into a uniform set, every tile kernel
     (2, (64, 48), 4000, 2, 1, np.complex64, 1e-6, "edges"),
     (2, (64, 48), 4000, 2, 2, np.complex64, 1e-6, "edges"),
