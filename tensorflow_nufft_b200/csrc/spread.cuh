@@ -273,8 +273,9 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   // REDG.ADD.F32x4 with index wrap, untouched (zero) pairs skipped.
   if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
       (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]))) {
+    fence_proxy_async_smem();   // every thread: its generic-proxy tile writes -> visible to the TMA unit
+    __syncthreads();
     if (tid == 0) {
-      fence_proxy_async_smem();
       if (RANK == 2) tma_reduce_add_3d(&tmap_out, tile4, 2 * ox, oy, t);
       else tma_reduce_add_4d(&tmap_out, tile4, 2 * ox, oy, oz, t);
       tma_store_commit_and_wait_read();

@@ -262,9 +262,9 @@ spread_ws_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   // pairs skipped).
   if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
       (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]))) {
+    fence_proxy_async_smem();   // every lane: its generic-proxy tile writes -> visible to the TMA unit
     __syncwarp();
     if (lane == 0) {
-      fence_proxy_async_smem();
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
         if (RANK == 2) tma_reduce_add_3d(&tmap_out, tile4 + k * (ncell / 2), 2 * ox, oy, t * NC + k);

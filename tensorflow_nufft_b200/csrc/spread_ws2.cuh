@@ -178,9 +178,9 @@ spread_ws2_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   // adds it to the fine grid in L2; no LSU work at all). Tiles that straddle the periodic boundary:
   // two complex cells per REDG.ADD.F32x4 with index wrap, zero pairs skipped.
   if (use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1]) {
+    fence_proxy_async_smem();   // every lane: its generic-proxy tile writes -> visible to the TMA unit
     __syncwarp();
     if (lane == 0) {
-      fence_proxy_async_smem();   // the warp's generic-proxy tile writes -> visible to the TMA unit
 #pragma unroll
       for (int k = 0; k < NC; ++k) tma_reduce_add_3d(&tmap_out, tile4 + k * (ncell / 2), 2 * ox, oy, t * NC + k);
       tma_store_commit_and_wait_read();   // the tile must stay allocated until it has been read
