@@ -196,7 +196,11 @@ void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
 // Tile-kernel dispatch on the kernel width.
 // ------------------------------------------------------------------------------------------
 constexpr int kInterpWarps = 4;
-constexpr int kSpreadWarps3D = 4;   // warps sharing one 3D tile (z-plane ownership)
+// Warps sharing one 3D tile (z-plane ownership). 1: every warp owns its tile and updates all 7
+// planes of a point (7 independent load/FFMA/store chains per lane) and the per-point record is
+// read once instead of once per warp; measured on cfg3 with the TMA flush: 2.39 ms (1 warp),
+// 2.59 ms (2), 2.79 ms (4).
+constexpr int kSpreadWarps3D = 1;
 
 bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr);
 
