@@ -181,7 +181,8 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
     raise RuntimeError("tensorflow_nufft_b200 needs a CUDA device; there is no CPU fallback")
   host_io = not source.is_cuda
   device = source.device if source.is_cuda else torch.device("cuda", torch.cuda.current_device())
-  if (host_io and op_type == "nufft" and not outer and num_transforms > _HOST_CHUNK and
+  if (host_io and op_type == "nufft" and not outer and
+      num_transforms > _host_chunk(source, num_transforms, num_points, grid_shape) and
       all(d != 0 for d in target_shape) and source.is_contiguous()):
     return _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, options,
                                num_transforms, num_points, target_shape, device, engine_kwargs)
@@ -275,13 +276,25 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
   return _to_host(tgt) if host_io else tgt
 
 
-_HOST_CHUNK = 8   # transforms per pipelined chunk (= the engine's batch size)
+_HOST_CHUNK = 8                   # transforms per pipelined chunk for small transforms
+_HOST_CHUNK_BYTES = 128 << 20     # ... and about this many bytes per chunk for large ones
+
+
+def _host_chunk(source, num_transforms, num_points, grid_shape):
+  """Transforms per pipelined chunk: 8 for 2D-sized transforms (cfg2: 16 MB of strengths each),
+  fewer when one transform is already tens of MB (cfg4: a 256^3 grid is 134 MB -> one per chunk,
+  so that the copy of coil k+1 overlaps the transform of coil k)."""
+  n_coeffs = 1
+  for g in grid_shape:
+    n_coeffs *= g
+  per = max(num_points, n_coeffs) * source.element_size()
+  return max(1, min(_HOST_CHUNK, _HOST_CHUNK_BYTES // max(per, 1)))
 
 
 def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, options, num_transforms,
                         num_points, target_shape, device, engine_kwargs):
   """Host-resident inputs, many transforms sharing one point set: the coils are streamed through
-  the GPU in chunks of _HOST_CHUNK with the H2D copy of chunk k+1, the transform of chunk k and
+  the GPU in chunks (`_host_chunk`) with the H2D copy of chunk k+1, the transform of chunk k and
   the D2H copy of chunk k-1 overlapped on three CUDA streams (the PCIe copies dominate: 8 bytes
   per point-transform each way)."""
   dev_index = device.index if device.index is not None else torch.cuda.current_device()
@@ -301,7 +314,7 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
     opt_kwargs.update(engine_kwargs)
   dcode = _lib.COMPLEX64 if source.dtype == torch.complex64 else _lib.COMPLEX128
   sign = -1 if fft_direction == "forward" else 1
-  chunk = _HOST_CHUNK
+  chunk = _host_chunk(source, T, num_points, grid_shape)
   # Chunk schedule: full chunks, then the last full chunk's worth is halved so that the part of the
   # pipeline that cannot overlap (the last transform + its D2H copy) is short.
   sizes = [chunk] * (T // chunk)

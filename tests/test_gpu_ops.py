@@ -242,6 +242,25 @@ def test_host_pipelined_chunks_match_device_path(ttype):
     assert H.rel_l2(out_h.numpy(), out_d.cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("ttype", ["type_1", "type_2"])
+def test_host_pipelined_single_transform_chunks(ttype, monkeypatch):
+  """Large transforms are streamed one per chunk (cfg4: a 256^3 grid per coil); forced here on a
+  small 3D case by shrinking the chunk byte target."""
+  tfft = _tfft()
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  monkeypatch.setattr(nufft_ops, "_HOST_CHUNK_BYTES", 1024)
+  grid = (12, 16, 10)
+  M = 3000
+  T = 3
+  pts = torch.from_numpy(H.uniform_points(M, 3, 15))
+  src = torch.from_numpy(H.random_complex((T, M) if ttype == "type_1" else (T,) + grid, 16))
+  assert nufft_ops._host_chunk(src, T, M, grid) == 1
+  out_h = tfft.nufft(src.pin_memory(), pts, grid_shape=grid, transform_type=ttype)
+  out_d = tfft.nufft(src.cuda(), pts.cuda(), grid_shape=grid, transform_type=ttype)
+  assert out_h.shape == out_d.shape and not out_h.is_cuda
+  assert H.rel_l2(out_h.numpy(), out_d.cpu().numpy()) < 1e-6
+
+
 def test_empty_inputs():
   tfft = _tfft()
   out = tfft.nufft(torch.zeros((0,), dtype=torch.complex64).cuda(), torch.zeros((0, 2), dtype=torch.float32).cuda(),
