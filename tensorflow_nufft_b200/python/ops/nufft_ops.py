@@ -181,9 +181,11 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
     raise RuntimeError("tensorflow_nufft_b200 needs a CUDA device; there is no CPU fallback")
   host_io = not source.is_cuda
   device = source.device if source.is_cuda else torch.device("cuda", torch.cuda.current_device())
-  if (host_io and op_type == "nufft" and not outer and
-      num_transforms > _host_chunk(source, num_transforms, num_points, grid_shape) and
-      all(d != 0 for d in target_shape) and source.is_contiguous()):
+  # Host-resident inputs sharing one point set always take the streamed path: even a single chunk
+  # gains the overlap of the strengths copy with the points copy + set_points.
+  if (host_io and op_type == "nufft" and not outer and num_points > 0 and
+      all(d != 0 for d in target_shape) and source.is_contiguous() and
+      source.numel() * source.element_size() >= _HOST_STREAM_MIN_BYTES):
     return _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, options,
                                num_transforms, num_points, target_shape, device, engine_kwargs)
   src = source.to(device, non_blocking=True) if host_io else source
@@ -276,6 +278,7 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
   return _to_host(tgt) if host_io else tgt
 
 
+_HOST_STREAM_MIN_BYTES = 8 << 20  # below this the plain copy-in / transform / copy-out path is used
 _HOST_CHUNK = 8                   # transforms per pipelined chunk for small transforms
 _HOST_CHUNK_BYTES = 128 << 20     # ... and about this many bytes per chunk for large ones
 
@@ -314,7 +317,7 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
     opt_kwargs.update(engine_kwargs)
   dcode = _lib.COMPLEX64 if source.dtype == torch.complex64 else _lib.COMPLEX128
   sign = -1 if fft_direction == "forward" else 1
-  chunk = _host_chunk(source, T, num_points, grid_shape)
+  chunk = min(T, _host_chunk(source, T, num_points, grid_shape))
   # Chunk schedule: full chunks, then the last full chunk's worth is halved so that the part of the
   # pipeline that cannot overlap (the last transform + its D2H copy) is short.
   sizes = [chunk] * (T // chunk)

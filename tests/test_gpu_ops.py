@@ -213,8 +213,11 @@ def test_point_set_reuse_skips_set_points_and_tracks_in_place_updates():
   tfft.set_points_reuse(True)
 
 
-def test_host_tensors_round_trip():
+@pytest.mark.parametrize("stream_min", [0, 1 << 40])
+def test_host_tensors_round_trip(stream_min, monkeypatch):
   tfft = _tfft()
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  monkeypatch.setattr(nufft_ops, "_HOST_STREAM_MIN_BYTES", stream_min)   # streamed and plain host paths
   src = torch.from_numpy(H.random_complex((3, 24, 20), 11))
   pts = torch.from_numpy(H.uniform_points(777, 2, 12))
   out_h = tfft.nufft(src, pts)
@@ -224,10 +227,12 @@ def test_host_tensors_round_trip():
 
 
 @pytest.mark.parametrize("ttype", ["type_1", "type_2"])
-def test_host_pipelined_chunks_match_device_path(ttype):
-  """Host-resident batches larger than one chunk are streamed (H2D / transform / D2H overlapped);
-  the result must be bit-identical to the all-on-device call."""
+def test_host_pipelined_chunks_match_device_path(ttype, monkeypatch):
+  """Host-resident batches are streamed (H2D / transform / D2H overlapped); the result must be
+  bit-identical to the all-on-device call."""
   tfft = _tfft()
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  monkeypatch.setattr(nufft_ops, "_HOST_STREAM_MIN_BYTES", 0)
   grid = (40, 36)
   M = 5000
   T = 20   # two full chunks of 8 and a remainder of 4
@@ -249,6 +254,7 @@ def test_host_pipelined_single_transform_chunks(ttype, monkeypatch):
   tfft = _tfft()
   from tensorflow_nufft_b200.python.ops import nufft_ops
   monkeypatch.setattr(nufft_ops, "_HOST_CHUNK_BYTES", 1024)
+  monkeypatch.setattr(nufft_ops, "_HOST_STREAM_MIN_BYTES", 0)
   grid = (12, 16, 10)
   M = 3000
   T = 3
