@@ -22,7 +22,7 @@
 #include "host_params.h"
 #include "interp.cuh"
 #include "interp_qw.cuh"
-#include "rowlane_f64.cuh"
+#include "rowlane.cuh"
 #include "points.cuh"
 #include "scan_sort.cuh"
 #include "spread.cuh"
@@ -86,7 +86,7 @@ struct b200nufft_plan {
     bool ok = false;
   };
   TileMap tmap_in, tmap_out;
-  RowLaneGeom rl{};        // complex128 2D tile kernels
+  RowLaneGeom rl{};        // row-lane 2D tile kernels (complex128; complex64 with ns > 7)
   int rl_pxt = 0, rl_lp = 0;
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
@@ -384,18 +384,19 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const double2* fw, double2* c, cudaStream_t st) {
+template <typename F>
+cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* fw, Cplx<F>* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->rl.TX, p->rl.TY, 1)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
-  const size_t smem = rowlane_smem_bytes(p->rl);
+  const size_t smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
 #define RL_CASE(PXT, LP)                                                                         \
   if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
-    auto k = interp_rowlane_f64_kernel<PXT, LP, 4>;                                              \
+    auto k = interp_rowlane_kernel<F, PXT, LP, 4>;                                               \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 128, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,   \
-                               p->start.as<int4>(), p->wrec.as<double>(), fw, c, p->tmap_in.map, use_tma); \
+                               p->start.as<int4>(), p->wrec.as<F>(), fw, c, p->tmap_in.map, use_tma); \
     return cudaGetLastError();                                                                   \
   }
   RL_CASE(8, 8) RL_CASE(12, 8) RL_CASE(12, 16) RL_CASE(16, 16)
@@ -403,17 +404,18 @@ cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const double2* fw,
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const double2* c, double2* fw, cudaStream_t st) {
+template <typename F>
+cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* c, Cplx<F>* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
-  const size_t smem = rowlane_smem_bytes(p->rl);
+  const size_t smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
 #define RL_CASE(PXT, LP)                                                                         \
   if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
-    auto k = spread_rowlane_f64_kernel<PXT, LP>;                                                 \
+    auto k = spread_rowlane_kernel<F, PXT, LP>;                                                  \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,    \
-                              p->start.as<int4>(), p->wrec.as<double>(), c, fw);                 \
+                              p->start.as<int4>(), p->wrec.as<F>(), c, fw);                      \
     return cudaGetLastError();                                                                   \
   }
   RL_CASE(8, 8) RL_CASE(12, 8) RL_CASE(12, 16) RL_CASE(16, 16)
@@ -425,7 +427,7 @@ template <typename F>
 int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
   if (p->spread_method == 5) {
-    cudaError_t e = launch_spread_rowlane(p, ntr, static_cast<const double2*>(c), static_cast<double2*>(fw), st);
+    cudaError_t e = launch_spread_rowlane<F>(p, ntr, static_cast<const Cplx<F>*>(c), static_cast<Cplx<F>*>(fw), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread rowlane launch: %s", cudaGetErrorString(e));
   } else if (p->spread_method == 4) {
     cudaError_t e;
@@ -474,7 +476,7 @@ template <typename F>
 int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t st) {
   if (p->M == 0) return B200NUFFT_OK;
   if (p->interp_method == 5) {
-    cudaError_t e = launch_interp_rowlane(p, ntr, static_cast<const double2*>(fw), static_cast<double2*>(c), st);
+    cudaError_t e = launch_interp_rowlane<F>(p, ntr, static_cast<const Cplx<F>*>(fw), static_cast<Cplx<F>*>(c), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp rowlane launch: %s", cudaGetErrorString(e));
   } else if (p->interp_method >= 3) {
     const float2* ff = static_cast<const float2*>(fw);
@@ -794,8 +796,9 @@ int create_impl(b200nufft_plan* p) {
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
-  // complex128 in 2D: row-lane tile kernels (rowlane_f64.cuh) unless the generic kernels are asked for
-  const bool rl_ok = p->is_double && p->rank == 2 && ns <= 15;
+  // 2D complex128, and 2D complex64 with widths the float tile kernels do not cover (ns 8..15):
+  // row-lane tile kernels (rowlane.cuh) unless the generic kernels are asked for
+  const bool rl_ok = p->rank == 2 && ns <= 15 && (p->is_double || ns > 7);
   if (rl_ok) {
     if (p->opts.spread_method != 1) p->spread_method = 5;
     if (p->opts.interp_method != 1) p->interp_method = 5;
@@ -844,8 +847,8 @@ int create_impl(b200nufft_plan* p) {
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
   if (rl_ok && (p->spread_method == 5 || p->interp_method == 5)) {
-    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX, p->PY);
-    p->tile_smem = rowlane_smem_bytes(p->rl);
+    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX, p->PY, p->is_double ? 0 : 1);
+    p->tile_smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
     if (p->tile_smem > 227 * 1024) {   // user-chosen bins too large: fall back to the generic kernels
       p->spread_method = 1;
       p->interp_method = 1;

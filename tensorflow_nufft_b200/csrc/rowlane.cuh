@@ -1,11 +1,11 @@
-// rowlane_f64.cuh -- shared-memory tile kernels for complex128 in 2D (any kernel width <= 15).
+// rowlane.cuh -- shared-memory tile kernels in 2D for the cases the float tile kernels do not
+// cover: complex128 (any kernel width <= 15) and complex64 with widths 8..15 (tol < 1e-6).
 //
 // Same sums as spread.cuh / interp.cuh (reference: SpreadSubproblem2DKernel / InterpSubproblem2DKernel
-// nufft_plan.cu.cc:790-878, 1041-1110), for the precision and widths the float tile kernels do not
-// cover (tol 1e-12 -> ns = 14: 196 cells of 16 bytes per point). Layout: one lane per ROW of the
-// stencil window, each lane walks PXT cells of its row with 128-bit accesses (one complex128 cell
-// each); the tile pitch is ODD in cells, so the 8 row-lanes of a quarter warp hit 8 distinct
-// 16-byte bank groups. The weight record is zero-padded to PXT x LP, so no lane needs the width.
+// nufft_plan.cu.cc:790-878, 1041-1110) (tol 1e-12 -> ns = 14: 196 cells of 16 bytes per point).
+// Layout: one lane per ROW of the stencil window, each lane walks PXT cells of its row, one
+// complex cell per access (128-bit for complex128, 64-bit for complex64); the tile pitch is ODD
+// in cells, so the row-lanes of a quarter (half) warp hit distinct bank groups. The weight record is zero-padded to PXT x LP, so no lane needs the width.
 //   * interp: LP lanes per point, 32 / LP points per warp instruction, shuffle reduction over the
 //     rows, weights read straight from the sorted record array; tile staged by TMA (interior) or
 //     wrapped cp.async.
@@ -29,11 +29,12 @@ struct RowLaneGeom {
   int R, PX, PY;  // record stride, wy offset and wy length, in reals (rows >= PY carry no weight)
 };
 
-inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, int PX, int PY) {
+// align_x: the records' x start is moved down to an even cell (complex64): one more halo cell.
+inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, int PX, int PY, int align_x) {
   RowLaneGeom r;
-  r.hx = (ns + 1) / 2;
+  r.hx = (ns + 1) / 2 + (align_x ? 1 : 0);
   r.hy = (ns + 1) / 2;
-  r.TX = (bin[0] + pxt + 2) | 1;
+  r.TX = (bin[0] + pxt + 2 + (align_x ? 2 : 0)) | 1;
   r.TY = bin[1] + lp + 2;
   r.R = R;
   r.PX = PX;
@@ -41,21 +42,23 @@ inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, 
   return r;
 }
 
-inline size_t rowlane_smem_bytes(const RowLaneGeom& r) {
-  return ((static_cast<size_t>(r.TX) * r.TY * sizeof(double2) + 127) & ~static_cast<size_t>(127)) + 16;
+inline size_t rowlane_smem_bytes(const RowLaneGeom& r, size_t cell_bytes) {
+  return ((static_cast<size_t>(r.TX) * r.TY * cell_bytes + 127) & ~static_cast<size_t>(127)) + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
 // type 2
 // ------------------------------------------------------------------------------------------------
-template <int PXT, int LP, int WARPS>
+template <typename F, int PXT, int LP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
-                          const int4* __restrict__ sub_desc, const int* __restrict__ idx,
-                          const int4* __restrict__ start, const double* __restrict__ wrec,
-                          const double2* __restrict__ fw, double2* __restrict__ c,
-                          const __grid_constant__ CUtensorMap tmap, int use_tma) {
-  extern __shared__ __align__(128) double2 tile_rl[];
+interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
+                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                      const int4* __restrict__ start, const F* __restrict__ wrec,
+                      const Cplx<F>* __restrict__ fw, Cplx<F>* __restrict__ c,
+                      const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  using C = Cplx<F>;
+  extern __shared__ __align__(128) unsigned char tile_raw[];
+  C* tile_rl = reinterpret_cast<C*>(tile_raw);
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -67,16 +70,16 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
   const int by = b / g.nbins[0];
   const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy;
   const int ncell = TX * TY;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(tile_rl) + ((static_cast<size_t>(ncell) * sizeof(double2) + 127) & ~static_cast<size_t>(127)));
-  const double2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
-  double2* ct = c + static_cast<int64_t>(t) * M;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(tile_rl) + ((static_cast<size_t>(ncell) * sizeof(C) + 127) & ~static_cast<size_t>(127)));
+  const C* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+  C* ct = c + static_cast<int64_t>(t) * M;
 
   const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1];
   if (interior) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(bar, static_cast<uint32_t>(ncell * sizeof(double2)));
+      mbar_expect_tx(bar, static_cast<uint32_t>(ncell * sizeof(C)));
       tma_load_3d(tile_rl, &tmap, bar, 2 * ox, oy, t);
     }
     mbar_wait(bar, 0);
@@ -86,7 +89,7 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
       const int iy = i / TX;
       const int gx = mod_idx(ox + ix, g.nf[0]);
       const int gy = mod_idx(oy + iy, g.nf[1]);
-      __pipeline_memcpy_async(&tile_rl[i], fwt + static_cast<int64_t>(gy) * g.nf[0] + gx, 16);
+      __pipeline_memcpy_async(&tile_rl[i], fwt + static_cast<int64_t>(gy) * g.nf[0] + gx, sizeof(C));
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -100,7 +103,7 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
   for (int grp = warp; grp < ngrp; grp += WARPS) {
     const int p = grp * PW + pt;
     const bool valid = p < np;
-    double re = 0.0, im = 0.0;
+    F re = F(0), im = F(0);
     int id = 0;
     if (valid) {
       const int64_t j = static_cast<int64_t>(p0) + p;
@@ -110,13 +113,13 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
       // Memory safety for coordinates outside the declared points_range (see interp.cuh).
       const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY;
       if (fits) {
-        const double* wx = wrec + j * rl.R;
-        const double wy = row < rl.PY ? wx[rl.PX + row] : 0.0;
-        const double2* ptr = tile_rl + (ry + row) * TX + rx;
+        const F* wx = wrec + j * rl.R;
+        const F wy = row < rl.PY ? wx[rl.PX + row] : F(0);
+        const C* ptr = tile_rl + (ry + row) * TX + rx;
 #pragma unroll
         for (int k = 0; k < PXT; k += 2) {
-          const double2 w2 = *reinterpret_cast<const double2*>(wx + k);
-          const double2 v0 = ptr[k], v1 = ptr[k + 1];
+          const C w2 = *reinterpret_cast<const C*>(wx + k);   // two consecutive weights
+          const C v0 = ptr[k], v1 = ptr[k + 1];
           re += v0.x * w2.x + v1.x * w2.y;
           im += v0.y * w2.x + v1.y * w2.y;
         }
@@ -129,7 +132,7 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
       re += __shfl_xor_sync(0xffffffffu, re, o);
       im += __shfl_xor_sync(0xffffffffu, im, o);
     }
-    if (valid && row == 0) ct[id] = make_double2(re, im);
+    if (valid && row == 0) ct[id] = make_cplx<F>(re, im);
   }
 }
 
@@ -137,13 +140,15 @@ interp_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
 // type 1: one-warp CTAs, private tile, one point per step. lane = half * 16 + row (LP <= 16):
 // a quarter warp = 8 consecutive rows of the same half-row, conflict-free with the odd pitch.
 // ------------------------------------------------------------------------------------------------
-template <int PXT, int LP>
+template <typename F, int PXT, int LP>
 __global__ void __launch_bounds__(32)
-spread_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
-                          const int4* __restrict__ sub_desc, const int* __restrict__ idx,
-                          const int4* __restrict__ start, const double* __restrict__ wrec,
-                          const double2* __restrict__ c, double2* __restrict__ fw) {
-  extern __shared__ __align__(128) double2 tile_rl[];
+spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
+                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                      const int4* __restrict__ start, const F* __restrict__ wrec,
+                      const Cplx<F>* __restrict__ c, Cplx<F>* __restrict__ fw) {
+  using C = Cplx<F>;
+  extern __shared__ __align__(128) unsigned char tile_raw[];
+  C* tile_rl = reinterpret_cast<C*>(tile_raw);
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
   const int lane = threadIdx.x;
@@ -155,10 +160,10 @@ spread_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
   const int by = b / g.nbins[0];
   const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy;
   const int ncell = TX * TY;
-  const double2* ct = c + static_cast<int64_t>(t) * M;
-  double2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+  const C* ct = c + static_cast<int64_t>(t) * M;
+  C* fwt = fw + static_cast<int64_t>(t) * g.nftot;
 
-  for (int i = lane; i < ncell; i += 32) tile_rl[i] = make_double2(0.0, 0.0);
+  for (int i = lane; i < ncell; i += 32) tile_rl[i] = make_cplx<F>(F(0), F(0));
   __syncwarp();
 
   constexpr int HW = PXT / 2;          // cells per half row
@@ -167,39 +172,39 @@ spread_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
   const bool row_ok = row < LP;
 
   // one-point software pipeline: the record of point p + 1 is fetched while point p is applied
-  double wxh[HW];
-  double wy = 0.0;
+  F wxh[HW];
+  F wy = F(0);
   int4 st = make_int4(0, 0, 0, 0);
-  double2 cj = make_double2(0.0, 0.0);
+  C cj = make_cplx<F>(F(0), F(0));
   auto fetch = [&](int p) {
     if (p < np) {
       const int64_t j = static_cast<int64_t>(p0) + p;
-      const double* wx = wrec + j * rl.R;
+      const F* wx = wrec + j * rl.R;
 #pragma unroll
       for (int k = 0; k < HW; k += 2) {
-        const double2 w2 = *reinterpret_cast<const double2*>(wx + half * HW + k);
+        const C w2 = *reinterpret_cast<const C*>(wx + half * HW + k);   // two consecutive weights
         wxh[k] = w2.x;
         wxh[k + 1] = w2.y;
       }
-      wy = (row_ok && row < rl.PY) ? wx[rl.PX + row] : 0.0;
+      wy = (row_ok && row < rl.PY) ? wx[rl.PX + row] : F(0);
       st = start[j];
       cj = ct[idx[j]];
     }
   };
   fetch(0);
   for (int p = 0; p < np; ++p) {
-    double w[HW];
+    F w[HW];
 #pragma unroll
     for (int k = 0; k < HW; ++k) w[k] = wxh[k];
-    const double cr = cj.x * wy, ci = cj.y * wy;
+    const F cr = cj.x * wy, ci = cj.y * wy;
     const int rx = st.x - ox, ry = st.y - oy;
     fetch(p + 1);
     // Memory safety for coordinates outside the declared points_range: such a window does not lie
     // in this bin's tile and the point is dropped (the reference's behaviour is undefined there).
     const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY;
     if (fits && row_ok) {
-      double2* ptr = tile_rl + (ry + row) * TX + rx + half * HW;
-      double2 v[HW];
+      C* ptr = tile_rl + (ry + row) * TX + rx + half * HW;
+      C v[HW];
 #pragma unroll
       for (int k = 0; k < HW; ++k) v[k] = ptr[k];
 #pragma unroll
@@ -212,10 +217,10 @@ spread_rowlane_f64_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __re
     __syncwarp();
   }
 
-  // flush: native f64 reductions, periodic wrap, untouched cells skipped
+  // flush: native global reductions (REDG.F64 / REDG.F32x2), periodic wrap, untouched cells skipped
   for (int i = lane; i < ncell; i += 32) {
-    const double2 v = tile_rl[i];
-    if (v.x == 0.0 && v.y == 0.0) continue;
+    const C v = tile_rl[i];
+    if (v.x == F(0) && v.y == F(0)) continue;
     const int ix = i % TX;
     const int iy = i / TX;
     const int gx = mod_idx(ox + ix, g.nf[0]);

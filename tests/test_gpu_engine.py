@@ -155,7 +155,11 @@ CASES = [
     (2, (64, 64), 20000, 2, 1, np.complex128, 1e-12, "uniform"),
     (3, (16, 20, 24), 5000, 1, 2, np.complex128, 1e-9, "uniform"),
     (3, (16, 20, 24), 5000, 1, 1, np.complex128, 1e-9, "uniform"),
-    (2, (64, 64), 20000, 1, 1, np.complex64, 1e-7, "uniform"),   # ns = 8: generic kernels
+    (2, (64, 64), 20000, 1, 1, np.complex64, 1e-7, "uniform"),   # ns = 8: float row-lane kernels
+    (2, (64, 64), 20000, 3, 2, np.complex64, 1e-7, "uniform"),
+    (2, (90, 50), 20000, 2, 1, np.complex64, 5e-8, "edges"),     # ns = 9 (tol clipped at 6e-8)
+    (2, (90, 50), 20000, 2, 2, np.complex64, 5e-8, "edges"),
+    (3, (16, 20, 12), 5000, 1, 2, np.complex64, 1e-7, "uniform"),  # 3D ns = 8: generic kernels
     # fine grids that are not multiples of the bin size (partial last bins, wrap inside a tile)
     (2, (135, 77), 30000, 3, 1, np.complex64, 1e-6, "uniform"),
     (2, (135, 77), 30000, 3, 2, np.complex64, 1e-6, "uniform"),
