@@ -19,6 +19,7 @@ def run(name, grid, pts, T, variants, reps=5, tol=1e-6):
     if "msub" in v: kw["max_subproblem_size"] = v["msub"]
     if "no_tma" in v: kw["no_tma"] = v["no_tma"]
     if "nc" in v: kw["coils_per_cta"] = v["nc"]
+    if "no_zrange" in v: kw["no_zrange"] = v["no_zrange"]
     try:
       plan = _lib.Plan(2, grid[::-1], -1, T, tol, 0, device=0, **kw)
     except Exception as e:

@@ -149,6 +149,8 @@ class Plan:
         opts.reserved[2] = int(v)
       elif k == "full_fft":
         opts.reserved[4] = int(v)
+      elif k == "no_zrange":
+        opts.reserved[6] = int(v)
       elif k == "no_tma_flush":
         opts.reserved[5] = int(v)
       else:

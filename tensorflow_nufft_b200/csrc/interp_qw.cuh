@@ -166,7 +166,7 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                      const int4* __restrict__ start, const float4* __restrict__ wrec4,
                      const float2* __restrict__ fw, float2* __restrict__ c,
-                     const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                     const __grid_constant__ CUtensorMap tmap, int use_tma, int zrange) {
   extern __shared__ __align__(128) float4 smem4[];
   const int s = blockIdx.x;
   if (s >= *sub_total) return;
@@ -189,16 +189,29 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   const float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
   const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
                         (RANK < 3 || (oz >= 0 && oz + TZ <= g.nf[2]));
+  // 3D: only the z-planes the subproblem's stencils reach are loaded (sub_desc.w, see
+  // subproblem_zrange_kernel); the tensor map's box is ONE plane and the planes complete on the
+  // same mbarrier. 2D: one box for the NC coil tiles.
+  int tz_lo = 0, tz_hi = TZ;
+  if (RANK == 3 && zrange) {
+    const int lo = (sd.w & 0xffff) - 32768 - oz, hi = ((sd.w >> 16) & 0xffff) - 32768 - oz + NS;
+    if (lo >= 0 && hi <= TZ && lo < hi) { tz_lo = lo; tz_hi = hi; }
+  }
+  const int plane_cells = TX * TY;
   if (interior) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(bar, static_cast<uint32_t>(NC * ncell * sizeof(float2)));
-      if (RANK == 2) tma_load_3d(tile4, &tmap, bar, 2 * ox, oy, t);
-      else tma_load_4d(tile4, &tmap, bar, 2 * ox, oy, oz, t);
+      if (RANK == 2) {
+        mbar_expect_tx(bar, static_cast<uint32_t>(NC * ncell * sizeof(float2)));
+        tma_load_3d(tile4, &tmap, bar, 2 * ox, oy, t);
+      } else {
+        mbar_expect_tx(bar, static_cast<uint32_t>((tz_hi - tz_lo) * plane_cells * sizeof(float2)));
+        for (int z = tz_lo; z < tz_hi; ++z) tma_load_4d(tile4 + z * (plane_cells / 2), &tmap, bar, 2 * ox, oy, oz + z, t);
+      }
     }
   } else {
-    for (int i = tid; i < ncell / 2; i += WARPS * 32) {
+    for (int i = tid + tz_lo * (plane_cells / 2); i < tz_hi * (plane_cells / 2); i += WARPS * 32) {
       const int ix = i % TXH;
       const int iy = (i / TXH) % TY;
       const int iz = i / (TXH * TY);

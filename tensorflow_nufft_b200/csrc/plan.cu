@@ -82,12 +82,14 @@ struct b200nufft_plan {
   struct TileMap {
     CUtensorMap map;
     const void* ptr = nullptr;
-    int batch = 0, box_x = 0, box_y = 0, coils = 0;
+    int batch = 0, box_x = 0, box_y = 0, box_z = 0, coils = 0;
     bool ok = false;
   };
   TileMap tmap_in, tmap_out;
   RowLaneGeom rl{};        // row-lane 2D tile kernels (complex128; complex64 with ns > 7)
   int rl_pxt = 0, rl_lp = 0;
+  bool adaptive_bin_z = false; // 3D type-2: bin depth chosen per point set (set_points)
+  bool zrange_valid = false;   // sub_desc.w holds the z extent of every subproblem (3D interp plans)
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
   size_t tile_smem = 0;
@@ -281,9 +283,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // Builds (or reuses) the tensor map of a grid batch [ntr][nf2][nf1][2*nf0] reals with a box of
 // box_x x box_y (x bin_z + 8) cells x box_coils transforms.
 bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const void* grid, int ntr,
-                     int box_x, int box_y, int box_coils) {
+                     int box_x, int box_y, int box_coils, int box_z = 0 /* 0: bin_z + 8 */) {
   if (tm->ok && tm->ptr == grid && tm->batch == ntr && tm->box_x == box_x && tm->box_y == box_y &&
-      tm->coils == box_coils)
+      tm->coils == box_coils && tm->box_z == box_z)
     return true;
   static EncodeTiledFn encode = nullptr;
   static bool tried = false;
@@ -307,7 +309,7 @@ bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const
   cuuint64_t row = static_cast<cuuint64_t>(p->nf[0]) * 2 * real_bytes;
   for (int d = 1; d < rank; ++d) {
     dims[d] = p->nf[d];
-    box[d] = d == 1 ? box_y : p->bin[d] + 8;
+    box[d] = d == 1 ? box_y : (box_z > 0 ? box_z : p->bin[d] + 8);
     strides[d - 1] = row;
     row *= p->nf[d];
   }
@@ -325,6 +327,7 @@ bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const
   tm->box_x = box_x;
   tm->box_y = box_y;
   tm->coils = box_coils;
+  tm->box_z = box_z;
   tm->ok = true;
   return true;
 }
@@ -363,7 +366,12 @@ constexpr int kQwWarps = 4;
 template <int RANK, int NC>
 cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->bin[0] + kQwHaloX, p->bin[1] + 8, NC)) ? 1 : 0;
+  // 3D: box of ONE z-plane (the kernel loads the planes its subproblem needs); needs 128-byte planes
+  const bool plane_ok = ((p->bin[0] + kQwHaloX) * (p->bin[1] + 8) * sizeof(float2)) % 128 == 0;
+  const int box_z = (RANK == 3 && plane_ok) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[0] == 0 && (RANK == 2 || plane_ok) &&
+                       ensure_tile_map(p, &p->tmap_in, fw, ntr, p->bin[0] + kQwHaloX, p->bin[1] + 8, NC, box_z)) ? 1 : 0;
+  const int zrange = (RANK == 3 && p->zrange_valid && p->opts.reserved[6] == 0) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = interp_qw_smem_bytes<RANK>(p->bin, NC);
 #define QW_CASE(NS)                                                                              \
@@ -373,7 +381,7 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kQwWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),        \
                                          p->idx, p->start.as<int4>(), p->wrec.as<float4>(),      \
-                                         fw, c, p->tmap_in.map, use_tma);                               \
+                                         fw, c, p->tmap_in.map, use_tma, zrange);                       \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -635,6 +643,22 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     return B200NUFFT_OK;
   }
   const int rank = p->rank;
+  if (p->adaptive_bin_z) {
+    // 3D interpolation: deep bins (16 x 8 x 8) when the point set is sparse in the fine grid --
+    // the per-CTA latency (descriptor, TMA round trip) is then amortised over 4x the points and
+    // the z-range trimming keeps the tile traffic at what the points reach (cfg4: 1.97 vs
+    // 2.11 ms) -- shallow bins (16 x 8 x 2) when it is dense (cfg3 as type 2: 1.18 vs 1.29 ms).
+    const int bz = static_cast<double>(M) < 0.15 * static_cast<double>(p->nftot) ? 8 : 2;
+    if (bz != p->bin[2]) {
+      p->bin[2] = bz;
+      p->nbins[2] = (p->nf[2] + bz - 1) / bz;
+      p->nbtot = p->nbins[0] * p->nbins[1] * p->nbins[2];
+    }
+  }
+  CUDA_OK(p, p->bin_sizes.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->bin_start.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->num_sub.reserve(sizeof(int) * (p->nbtot + 1)));
+  CUDA_OK(p, p->sub_start.reserve(sizeof(int) * (p->nbtot + 1)));
   CUDA_OK(p, p->folded.reserve(sizeof(F) * 4 * M));
   CUDA_OK(p, p->keys0.reserve(sizeof(uint32_t) * M));
   CUDA_OK(p, p->keys1.reserve(sizeof(uint32_t) * M));
@@ -730,6 +754,15 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   }
   LAUNCH_OK(p);
   p->launches++;
+
+  p->zrange_valid = false;
+  if (rank == 3 && !p->is_double && p->interp_method == 3 && (p->type == 2 || p->opts.spread_only) && p->sub_bound > 0) {
+    subproblem_zrange_kernel<<<ceil_div(p->sub_bound, 8), 256, 0, st>>>(p->sub_total(), p->start.as<int4>(),
+                                                                       p->sub_desc.as<int4>());
+    LAUNCH_OK(p);
+    p->launches++;
+    p->zrange_valid = true;
+  }
 
   if (prof) cudaEventRecord(p->ev[5], st);
   p->ev_setpts = prof;
@@ -832,6 +865,8 @@ int create_impl(b200nufft_plan* p) {
     p->nbins[d] = d < p->rank ? (p->nf[d] + p->bin[d] - 1) / p->bin[d] : 1;
     p->nbtot *= p->nbins[d];
   }
+  p->adaptive_bin_z = p->rank == 3 && p->type == 2 && !p->opts.spread_only && tile_ok && p->interp_method == 3 &&
+                      p->opts.bin_dims[2] == 0 && p->bin[0] == 16 && p->bin[1] == 8;
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && ws_any;

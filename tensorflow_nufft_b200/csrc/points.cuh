@@ -5,6 +5,8 @@
 // binsort_singlethread nufft_plan.cc:475-531 (CPU); stencil start/offset and direct ES
 // evaluation nufft_plan.cc:1187-1201,1254-1289 / nufft_plan.cu.cc:838-846.
 #pragma once
+#include <climits>
+
 #include "dev_common.cuh"
 
 namespace b200 {
@@ -189,6 +191,35 @@ subproblem_desc_kernel(const int* __restrict__ bin_sizes, const int* __restrict_
   const int s0 = sub_start[b], p0 = bin_start[b];
   for (int k = 0; k < n; ++k)
     sub_desc[s0 + k] = make_int4(b, p0 + k * msub, min(msub, size - k * msub), 0);
+}
+
+// z extent of every subproblem's stencils (3D type-2 plans): sub_desc[s].w = zmin | (zmax << 16),
+// the smallest / largest stencil z start (fine-grid index + 32768 offset so that negative starts
+// pack) over the subproblem's points. The interpolator then loads only the planes
+// [zmin, zmax + ns) of the tile instead of all bin_z + 8: a stack-of-stars bin holds one k_z, i.e.
+// 7 of its 10 planes. One warp per subproblem.
+__global__ void __launch_bounds__(256)
+subproblem_zrange_kernel(const int* __restrict__ sub_total, const int4* __restrict__ start,
+                         int4* __restrict__ sub_desc) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= *sub_total) return;
+  const int lane = threadIdx.x & 31;
+  const int4 sd = sub_desc[s];
+  int zmin = INT_MAX, zmax = INT_MIN;
+  for (int p = lane; p < sd.z; p += 32) {
+    const int z = start[sd.y + p].z;
+    zmin = min(zmin, z);
+    zmax = max(zmax, z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    zmin = min(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+    zmax = max(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+  }
+  if (lane == 0) {
+    const int lo = max(0, min(65535, zmin + 32768)), hi = max(0, min(65535, zmax + 32768));
+    sub_desc[s].w = lo | (hi << 16);
+  }
 }
 
 // ES kernel value phi(x) = exp(beta * sqrt(1 - c x^2)) for |x| < ns/2, else 0, with the
