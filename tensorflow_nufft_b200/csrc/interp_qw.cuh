@@ -63,7 +63,7 @@ __device__ __forceinline__ float qw_reduce(float (&v)[N], int lane) {
 // k * ncell / 2 float4; origin ox, oy, oz; pitch TX cells). Groups of 4 points are dealt
 // round-robin to the `nwarps` warps. Records are read from global memory (sorted order, base
 // index p0) ONCE for the NC coils. Output: ct[k * M + id].
-template <int NS, int RANK, int NC, typename WaitTile>
+template <int NS, int RANK, int NC, int PF, typename WaitTile>
 __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __restrict__ tile4, int TX, int TY, int TZ, int ox, int oy, int oz,
                                           int p0, int np, int warp, int nwarps, int lane,
                                           const int* __restrict__ idx, const int4* __restrict__ start,
@@ -78,34 +78,52 @@ __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __
   const int tile_f4 = zstride4 * TZ;
   const int ngrp = (np + 3) >> 2;
 
-  float4 wxa, wxb, wza, wzb;
-  float wy = 0.f;
-  int4 st = make_int4(0, 0, 0, 0);
-  int id = 0;
-  wxa = wxb = wza = wzb = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Per-lane record of one point, prefetched PF groups ahead. PF = 2 on sparse 3D point sets (the
+  // records stream from DRAM and one group of gathers is shorter than a DRAM round trip: cfg4
+  // 1.97 -> 1.83 ms); PF = 1 elsewhere (the extra 24 registers cost a resident CTA: cfg3 as type 2
+  // 1.20 -> 1.27 ms with PF = 2).
+  struct Rec {
+    float4 wxa, wxb, wza, wzb;
+    float wy;
+    int4 st;
+    int id;
+  };
   auto fetch = [&](int grp) {
+    Rec r;
+    r.wxa = r.wxb = r.wza = r.wzb = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.wy = 0.f;
+    r.st = make_int4(0, 0, 0, 0);
+    r.id = 0;
     const int p = 4 * grp + pt;
     if (grp < ngrp && p < np) {
       const int64_t j = static_cast<int64_t>(p0) + p;
-      wxa = wrec4[j * C4];
-      wxb = wrec4[j * C4 + 1];
-      wy = reinterpret_cast<const float*>(wrec4 + j * C4 + 2)[row];
+      r.wxa = wrec4[j * C4];
+      r.wxb = wrec4[j * C4 + 1];
+      r.wy = reinterpret_cast<const float*>(wrec4 + j * C4 + 2)[row];
       if (RANK > 2) {
-        wza = wrec4[j * C4 + 4];
-        wzb = wrec4[j * C4 + 5];
+        r.wza = wrec4[j * C4 + 4];
+        r.wzb = wrec4[j * C4 + 5];
       }
-      st = start[j];
-      id = idx[j];
+      r.st = start[j];
+      r.id = idx[j];
     }
+    return r;
   };
-  fetch(warp);
+  Rec r1 = fetch(warp);
+  Rec r2 = r1;
+  if (PF == 2) r2 = fetch(warp + nwarps);
   wait_tile();   // the first records are in flight while the tile lands
   for (int grp = warp; grp < ngrp; grp += nwarps) {
-    const float4 xa = wxa, xb = wxb, za = wza, zb = wzb;
-    const float wy_c = wy;
-    const int4 st_c = st;
-    const int id_c = id;
-    fetch(grp + nwarps);
+    const float4 xa = r1.wxa, xb = r1.wxb, za = r1.wza, zb = r1.wzb;
+    const float wy_c = r1.wy;
+    const int4 st_c = r1.st;
+    const int id_c = r1.id;
+    if (PF == 2) {
+      r1 = r2;
+      r2 = fetch(grp + 2 * nwarps);
+    } else {
+      r1 = fetch(grp + nwarps);
+    }
 
     const bool valid = 4 * grp + pt < np;
     float v[NV];
@@ -160,7 +178,7 @@ __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __
 // CTAs of the SM hide the tile latency. (A persistent grid-stride variant and a two-stage tile ring
 // were measured slower on every BASELINE config: static striding loses the hardware scheduler's
 // load balancing between heavy and light subproblems.)
-template <int NS, int RANK, int NC, int WARPS>
+template <int NS, int RANK, int NC, int PF, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const int4* __restrict__ sub_desc, const int* __restrict__ idx,
@@ -232,7 +250,7 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
       __syncthreads();
     }
   };
-  qw_gather<NS, RANK, NC>(wait_tile, tile4, TX, TY, TZ, ox, oy, oz, p0, np, warp, WARPS, lane, idx, start, wrec4,
+  qw_gather<NS, RANK, NC, PF>(wait_tile, tile4, TX, TY, TZ, ox, oy, oz, p0, np, warp, WARPS, lane, idx, start, wrec4,
                           c + static_cast<int64_t>(t) * M, M);
 }
 

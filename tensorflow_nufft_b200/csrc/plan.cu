@@ -363,7 +363,7 @@ cudaError_t launch_interp_tile(b200nufft_plan* p, int ntr, const float2* fw, flo
 
 constexpr int kQwWarps = 4;
 
-template <int RANK, int NC>
+template <int RANK, int NC, int PF>
 cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   // 3D: box of ONE z-plane (the kernel loads the planes its subproblem needs); needs 128-byte planes
@@ -376,7 +376,7 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
   const size_t smem = interp_qw_smem_bytes<RANK>(p->bin, NC);
 #define QW_CASE(NS)                                                                              \
   case NS: {                                                                                     \
-    auto k = interp_qw_f32_kernel<NS, RANK, NC, kQwWarps>;                                       \
+    auto k = interp_qw_f32_kernel<NS, RANK, NC, PF, kQwWarps>;                                       \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, kQwWarps * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(),        \
@@ -494,11 +494,12 @@ int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t 
     const int nc_opt = p->opts.reserved[1];
     const int nc = nc_opt > 0 ? nc_opt : 8;
     cudaError_t e;
-    if (p->rank == 3) e = launch_interp_qw<3, 1>(p, ntr, ff, cc, st);
-    else if (nc >= 8 && ntr % 8 == 0) e = launch_interp_qw<2, 8>(p, ntr, ff, cc, st);
-    else if (nc >= 4 && ntr % 4 == 0) e = launch_interp_qw<2, 4>(p, ntr, ff, cc, st);
-    else if (nc >= 2 && ntr % 2 == 0) e = launch_interp_qw<2, 2>(p, ntr, ff, cc, st);
-    else e = launch_interp_qw<2, 1>(p, ntr, ff, cc, st);
+    if (p->rank == 3) e = p->bin[2] >= 8 ? launch_interp_qw<3, 1, 2>(p, ntr, ff, cc, st)    // deep bins = sparse set
+                                         : launch_interp_qw<3, 1, 1>(p, ntr, ff, cc, st);
+    else if (nc >= 8 && ntr % 8 == 0) e = launch_interp_qw<2, 8, 1>(p, ntr, ff, cc, st);
+    else if (nc >= 4 && ntr % 4 == 0) e = launch_interp_qw<2, 4, 1>(p, ntr, ff, cc, st);
+    else if (nc >= 2 && ntr % 2 == 0) e = launch_interp_qw<2, 2, 1>(p, ntr, ff, cc, st);
+    else e = launch_interp_qw<2, 1, 1>(p, ntr, ff, cc, st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp qw launch: %s", cudaGetErrorString(e));
   } else if (p->interp_method == 2) {
     cudaError_t e = p->rank == 2
