@@ -187,10 +187,13 @@ interp_qw_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                      const __grid_constant__ CUtensorMap tmap, int use_tma, int zrange) {
   extern __shared__ __align__(128) float4 smem4[];
   const int s = blockIdx.x;
-  if (s >= *sub_total) return;
+  // the subproblem count and this CTA's descriptor are independent loads (the descriptor
+  // array has an entry for every launched CTA): one global round trip instead of two
+  const int nsub_live = *sub_total;
+  const int4 sd = sub_desc[s];
+  if (s >= nsub_live) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y * NC;   // first transform of this CTA's group
-  const int4 sd = sub_desc[s];
   const int b = sd.x, p0 = sd.y, np = sd.z;
 
   const int TX = g.bin[0] + kQwHaloX, TY = g.bin[1] + 8;

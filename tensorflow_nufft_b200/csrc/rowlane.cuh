@@ -60,10 +60,13 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   extern __shared__ __align__(128) unsigned char tile_raw[];
   C* tile_rl = reinterpret_cast<C*>(tile_raw);
   const int s = blockIdx.x;
-  if (s >= *sub_total) return;
+  // the subproblem count and this CTA's descriptor are independent loads (the descriptor
+  // array has an entry for every launched CTA): one global round trip instead of two
+  const int nsub_live = *sub_total;
+  const int4 sd = sub_desc[s];
+  if (s >= nsub_live) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
-  const int4 sd = sub_desc[s];
   const int b = sd.x, p0 = sd.y, np = sd.z;
   const int TX = rl.TX, TY = rl.TY;
   const int bx = b % g.nbins[0];
@@ -150,10 +153,13 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   extern __shared__ __align__(128) unsigned char tile_raw[];
   C* tile_rl = reinterpret_cast<C*>(tile_raw);
   const int s = blockIdx.x;
-  if (s >= *sub_total) return;
+  // the subproblem count and this CTA's descriptor are independent loads (the descriptor
+  // array has an entry for every launched CTA): one global round trip instead of two
+  const int nsub_live = *sub_total;
+  const int4 sd = sub_desc[s];
+  if (s >= nsub_live) return;
   const int lane = threadIdx.x;
   const int t = blockIdx.y;
-  const int4 sd = sub_desc[s];
   const int b = sd.x, p0 = sd.y, np = sd.z;
   const int TX = rl.TX, TY = rl.TY;
   const int bx = b % g.nbins[0];

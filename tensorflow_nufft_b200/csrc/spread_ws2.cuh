@@ -35,10 +35,13 @@ spread_ws2_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
   extern __shared__ __align__(128) float4 smem4[];
 
   const int s = blockIdx.x;
-  if (s >= *sub_total) return;
+  // the subproblem count and this CTA's descriptor are independent loads (the descriptor
+  // array has an entry for every launched CTA): one global round trip instead of two
+  const int nsub_live = *sub_total;
+  const int4 sd = sub_desc[s];
+  if (s >= nsub_live) return;
   const int lane = threadIdx.x;
   const int t = blockIdx.y;
-  const int4 sd = sub_desc[s];
   const int b = sd.x, p0 = sd.y, np = sd.z;
 
   const int TX = g.bin[0] + 8, TY = g.bin[1] + 8;
