@@ -287,16 +287,15 @@ bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const
   if (tm->ok && tm->ptr == grid && tm->batch == ntr && tm->box_x == box_x && tm->box_y == box_y &&
       tm->coils == box_coils && tm->box_z == box_z)
     return true;
-  static EncodeTiledFn encode = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link), once per process
+  static const EncodeTiledFn encode = [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+      return reinterpret_cast<EncodeTiledFn>(fn);
+    return static_cast<EncodeTiledFn>(nullptr);
+  }();
   tm->ok = false;
   if (!encode) return false;
   const int rank = p->rank;
