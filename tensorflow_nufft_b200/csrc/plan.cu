@@ -204,21 +204,25 @@ constexpr int kInterpWarps = 4;
 // 2.59 ms (2), 2.79 ms (4).
 constexpr int kSpreadWarps3D = 1;
 
-bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr);
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z);
 
 template <int RANK, int WPT>
 cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = spread_tile_smem_bytes<RANK, WPT>(p->bin);
-  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
+  // 3D: one-plane boxes (the kernel sends the planes its subproblem touched); needs 128-byte planes
+  const bool plane_ok = ((p->bin[0] + 8) * (p->bin[1] + 8) * sizeof(float2)) % 128 == 0;
+  const int use_tma = (p->opts.reserved[5] == 0 && (RANK == 2 || plane_ok) &&
+                       ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, RANK == 3 ? 1 : 0)) ? 1 : 0;
+  const int zrange = (RANK == 3 && p->zrange_valid && p->opts.reserved[6] == 0) ? 1 : 0;
 #define SPREAD_CASE(NS)                                                                          \
   case NS: {                                                                                     \
     auto k = spread_tile_f32_kernel<NS, RANK, WPT>;                                              \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, WPT * 32, smem, st>>>(p->M, g, p->sub_total(), p->sub_desc.as<int4>(), p->idx,     \
-                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
+                                    p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma, zrange); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -234,7 +238,7 @@ cudaError_t launch_spread_ws(const b200nufft_plan* p, int ntr, const float2* c, 
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = spread_ws_smem_bytes<RANK, NC>(p->bin);
-  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, 0)) ? 1 : 0;
 #define WS_CASE(NS)                                                                              \
   case NS: {                                                                                     \
     auto k = spread_ws_f32_kernel<NS, RANK, TZ, NC>;                                             \
@@ -257,7 +261,7 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
   GridGeom g = grid_geom(p);
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr / NC);
   const size_t smem = spread_ws_smem_bytes<2, NC>(p->bin);
-  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr)) ? 1 : 0;
+  const int use_tma = (p->opts.reserved[5] == 0 && ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, 0)) ? 1 : 0;
 #define WS2_CASE(NS)                                                                             \
   case NS: {                                                                                     \
     auto k = spread_ws2_f32_kernel<NS, NC>;                                                          \
@@ -332,8 +336,8 @@ bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const
 }
 
 // The spreaders' output map: box = one (bin + 8)^rank tile of one transform.
-bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr) {
-  return ensure_tile_map(p, &p->tmap_out, grid, ntr, p->bin[0] + 8, p->bin[1] + 8, 1);
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z = 0) {
+  return ensure_tile_map(p, &p->tmap_out, grid, ntr, p->bin[0] + 8, p->bin[1] + 8, 1, box_z);
 }
 
 template <int RANK>
@@ -756,7 +760,9 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   p->launches++;
 
   p->zrange_valid = false;
-  if (rank == 3 && !p->is_double && p->interp_method == 3 && (p->type == 2 || p->opts.spread_only) && p->sub_bound > 0) {
+  const bool zr_interp = p->interp_method == 3 && (p->type == 2 || p->opts.spread_only);
+  const bool zr_spread = p->spread_method == 2 && (p->type == 1 || p->opts.spread_only);
+  if (rank == 3 && !p->is_double && (zr_interp || zr_spread) && p->sub_bound > 0) {
     subproblem_zrange_kernel<<<ceil_div(p->sub_bound, 8), 256, 0, st>>>(p->sub_total(), p->start.as<int4>(),
                                                                        p->sub_desc.as<int4>());
     LAUNCH_OK(p);

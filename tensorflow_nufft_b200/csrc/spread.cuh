@@ -116,7 +116,7 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
                        const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                        const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][2*RANK]*/,
                        const float2* __restrict__ c, float2* __restrict__ fw,
-                       const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
+                       const __grid_constant__ CUtensorMap tmap_out, int use_tma, int zrange) {
   constexpr int QX = (NS + 2) / 2;      // float4 lanes per stencil row: covers NS+1 cells
   static_assert(QX * NS <= 32, "stencil slab must fit one warp");
   constexpr int C4 = 2 * RANK;          // float4 chunks per weight record
@@ -279,8 +279,20 @@ spread_tile_f32_kernel(int64_t M, GridGeom g, const int* __restrict__ sub_total,
     fence_proxy_async_smem();   // every thread: its generic-proxy tile writes -> visible to the TMA unit
     __syncthreads();
     if (tid == 0) {
-      if (RANK == 2) tma_reduce_add_3d(&tmap_out, tile4, 2 * ox, oy, t);
-      else tma_reduce_add_4d(&tmap_out, tile4, 2 * ox, oy, oz, t);
+      if (RANK == 2) {
+        tma_reduce_add_3d(&tmap_out, tile4, 2 * ox, oy, t);
+      } else {
+        // 3D: the tensor-map box is ONE z-plane; only the planes the subproblem's stencils reach
+        // (sub_desc.w, subproblem_zrange_kernel) are sent: the reduce-add traffic in L2 is what
+        // bounds sparse point sets (a stack-of-stars bin holds one k_z: 7 of 10 planes).
+        int tz_lo = 0, tz_hi = TZ;
+        if (zrange) {
+          const int lo = (sd.w & 0xffff) - 32768 - oz, hi = ((sd.w >> 16) & 0xffff) - 32768 - oz + NS;
+          if (lo >= 0 && hi <= TZ && lo < hi) { tz_lo = lo; tz_hi = hi; }
+        }
+        for (int z = tz_lo; z < tz_hi; ++z)
+          tma_reduce_add_4d(&tmap_out, tile4 + z * (TX * TY / 2), 2 * ox, oy, oz + z, t);
+      }
       tma_store_commit_and_wait_read();
     }
     return;
