@@ -71,7 +71,12 @@ typedef struct b200nufft_opts {
                               lanes over one point's stencil, 3 shared-memory tiles, quarter warp
                               per point                                                           */
   int profile;             /* 1: record CUDA events around the stages (b200nufft_get_timings)     */
-  int reserved[8];
+  int reserved[8];         /* engine A/B switches used by the tests and probes (0 = default):
+                              [0] 1: stage interpolator tiles with cp.async instead of TMA
+                              [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8)
+                              [4] 3D FFT: 1 = single cuFFT 3D plan, 2 = same as 0 (pruned along z)
+                              [5] 1: flush spreader tiles with REDG instead of TMA reduce-add
+                              [6] 1: 3D tiles move all their z-planes (no per-subproblem z range) */
 } b200nufft_opts;
 
 typedef struct b200nufft_info {
