@@ -74,7 +74,7 @@ typedef struct b200nufft_opts {
   int reserved[8];         /* engine A/B switches used by the tests and probes (0 = default):
                               [0] 1: stage interpolator tiles with cp.async instead of TMA
                               [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8)
-                              [4] 3D FFT: 1 = single cuFFT 3D plan, 2 = same as 0 (pruned along z)
+                              [4] 1: single cuFFT 3D plan instead of the pruned three-plan scheme
                               [5] 1: flush spreader tiles with REDG instead of TMA reduce-add
                               [6] 1: 3D tiles move all their z-planes (no per-subproblem z range) */
 } b200nufft_opts;
