@@ -704,8 +704,6 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   LAUNCH_OK(p);
   p->idx = vs;
 
-  p->launches += exclusive_scan_i32(p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->nbtot,
-                                    p->scan_tmp(), nullptr, st);
   // Points per subproblem: the reference caps at 1024 (gpu_max_subproblem_size, nufft_options.h:153).
   // Small point sets get smaller subproblems so that the launch still fills the 148 SMs.
   if (p->opts.max_subproblem_size > 0) {
@@ -716,27 +714,28 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     while (ms < 1024 && ms < per_item) ms *= 2;
     p->msub = ms;
   }
+  // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
+  // launch the bound, surplus CTAs exit on the device-side count.
+  p->sub_bound = std::min<int64_t>(p->nbtot, M) + M / p->msub;
+  CUDA_OK(p, p->sub_desc.reserve(sizeof(int4) * (p->sub_bound + 1)));
   if (p->nbtot <= kScanSmallMax) {
-    scan_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
-                                         p->sub_total());
+    bins_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub, p->bin_start.as<int>(),
+                                         p->sub_start.as<int>(), p->sub_total(), p->sub_desc.as<int4>());
     p->launches++;
   } else {
+    p->launches += exclusive_scan_i32(p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->nbtot,
+                                      p->scan_tmp(), nullptr, st);
     subproblem_count_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub,
                                                                     p->num_sub.as<int>());
     p->launches++;
     p->launches += exclusive_scan_i32(p->num_sub.as<int>(), p->sub_start.as<int>(), p->nbtot, p->scan_tmp(),
                                       p->sub_total(), st);
+    subproblem_desc_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(
+        p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
+        p->sub_desc.as<int4>());
+    p->launches++;
   }
   LAUNCH_OK(p);
-  // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
-  // launch the bound, surplus CTAs exit on the device-side count.
-  p->sub_bound = std::min<int64_t>(p->nbtot, M) + M / p->msub;
-  CUDA_OK(p, p->sub_desc.reserve(sizeof(int4) * (p->sub_bound + 1)));
-  subproblem_desc_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(
-      p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
-      p->sub_desc.as<int4>());
-  LAUNCH_OK(p);
-  p->launches++;
 
   const int align_x = (!p->is_double) ? 1 : 0;
   const int align = align_x | (p->ws2 ? 2 : 0);

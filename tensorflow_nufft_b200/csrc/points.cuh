@@ -8,6 +8,7 @@
 #include <climits>
 
 #include "dev_common.cuh"
+#include "scan_sort.cuh"
 
 namespace b200 {
 
@@ -191,6 +192,45 @@ subproblem_desc_kernel(const int* __restrict__ bin_sizes, const int* __restrict_
   const int s0 = sub_start[b], p0 = bin_start[b];
   for (int k = 0; k < n; ++k)
     sub_desc[s0 + k] = make_int4(b, p0 + k * msub, min(msub, size - k * msub), 0);
+}
+
+// Small plans (bins <= kScanSmallMax, i.e. every 2D plan): bin offsets, subproblem offsets, the
+// subproblem count and the descriptors in ONE single-CTA kernel instead of three launches (the
+// launch-bound regime: cfg1 spends 0.06 of its 0.10 ms in set_points' ten tiny kernels).
+__global__ void __launch_bounds__(1024)
+bins_small_kernel(const int* __restrict__ bin_sizes, int nb, int msub, int* __restrict__ bin_start,
+                  int* __restrict__ sub_start, int* __restrict__ sub_total, int4* __restrict__ sub_desc) {
+  __shared__ int wsum[2][32];
+  __shared__ int carry_s[2];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < 2) carry_s[t] = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int b = base + t;
+    const int size = b < nb ? bin_sizes[b] : 0;
+    const int nsub = (size + msub - 1) / msub;
+    const int incl_a = warp_incl_scan(size);
+    const int incl_b = warp_incl_scan(nsub);
+    if (lane == 31) { wsum[0][warp] = incl_a; wsum[1][warp] = incl_b; }
+    __syncthreads();
+    if (warp < 2) {
+      const int sv = wsum[warp][lane];
+      const int si = warp_incl_scan(sv);
+      wsum[warp][lane] = si - sv;
+    }
+    __syncthreads();
+    const int p0 = carry_s[0] + wsum[0][warp] + incl_a - size;
+    const int s0 = carry_s[1] + wsum[1][warp] + incl_b - nsub;
+    if (b < nb) {
+      bin_start[b] = p0;
+      sub_start[b] = s0;
+      for (int k = 0; k < nsub; ++k) sub_desc[s0 + k] = make_int4(b, p0 + k * msub, min(msub, size - k * msub), 0);
+    }
+    __syncthreads();
+    if (t == 1023) { carry_s[0] = p0 + size; carry_s[1] = s0 + nsub; }
+    __syncthreads();
+  }
+  if (t == 0) *sub_total = carry_s[1];
 }
 
 // z extent of every subproblem's stencils (3D type-2 plans): sub_desc[s].w = zmin | (zmax << 16),
