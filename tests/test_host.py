@@ -189,3 +189,28 @@ def test_shard_bounds_cover_and_balance():
         assert a[1] == b[0]
       sizes = [e - b for b, e in spans]
       assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_stream_chunking_policy():
+  """Host-resident batches are streamed in chunks of 8 transforms when a transform is small
+  (cfg2: 16 MB of strengths) and of one transform when it is already >= the 128 MB chunk target
+  (cfg4: a 256^3 grid)."""
+  import torch
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  small = torch.zeros((2, 4), dtype=torch.complex64)
+  assert nufft_ops._host_chunk(small, 32, 2_000_000, (512, 512)) == 8          # cfg2
+  assert nufft_ops._host_chunk(small, 16, 4_000_000, (256, 256, 256)) == 1     # cfg4
+  assert nufft_ops._host_chunk(small, 4, 8_000_000, (128, 128, 128)) == 2      # 64 MB per transform
+  big = torch.zeros((2, 4), dtype=torch.complex128)
+  assert nufft_ops._host_chunk(big, 32, 2_000_000, (512, 512)) == 4            # 32 MB per transform
+  assert nufft_ops._host_chunk(small, 3, 10, (8, 8)) == 8
+
+
+def test_point_set_reuse_is_for_device_tensors_only():
+  """A host `points` tensor may alias a numpy array that changes behind torch's version counter:
+  it never yields a reuse token."""
+  import torch
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  pts = torch.zeros((10, 2))
+  assert nufft_ops._points_token(pts) is None
+  assert not nufft_ops._same_points(None, pts)
