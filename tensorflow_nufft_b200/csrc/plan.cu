@@ -125,7 +125,8 @@ struct b200nufft_plan {
 
   int* scan_tmp() const { return misc.as<int>(); }
   int* sub_total() const { return misc.as<int>() + kScanMaxBlocks; }
-  int* range_flag() const { return misc.as<int>() + kScanMaxBlocks + 1; }
+  // the range-check flag lives right behind the bin histogram so that one memset clears both
+  int* range_flag() const { return bin_sizes.as<int>() + nbtot; }
 };
 
 namespace {
@@ -683,8 +684,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.align_y = p->ws2 ? 1 : 0;
   const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY : 1);
 
-  CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * p->nbtot, st));
-  CUDA_OK(p, cudaMemsetAsync(p->range_flag(), 0, sizeof(int), st));
+  CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * (p->nbtot + 1), st));   // histogram + range flag
   F lo, hi;
   points_bounds<F>(p, &lo, &hi);
   const int check = p->opts.check_points_range && p->opts.points_range != B200NUFFT_RANGE_INFINITE;
