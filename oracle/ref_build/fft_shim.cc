@@ -3,6 +3,7 @@
 // image without FFTW. In-place, contiguous plan_many_dft only (all the reference uses,
 // nufft_plan.cc:413-426).
 #include <fftw3.h>
+#include <chrono>
 #include <cstdlib>
 extern "C" {
 void fft235_f32(float* data, int rank, const int* dims, int howmany, long dist, int sign, int nthreads);
@@ -10,6 +11,11 @@ void fft235_f64(double* data, int rank, const int* dims, int howmany, long dist,
 }
 namespace {
 int g_threads = 1;
+double g_fft_seconds = 0.0;   // wall time spent inside fftw[f]_execute since the last reset
+struct FftTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~FftTimer() { g_fft_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 struct PlanRec { int rank; int n[3]; int howmany; void* data; long dist; int sign; };
 PlanRec* make(int r, const int* n, int h, void* in, int dist, int sign) {
   PlanRec* p = new PlanRec{r, {1, 1, 1}, h, in, dist, sign};
@@ -42,11 +48,20 @@ fftw_plan fftw_plan_many_dft(int r, const int* n, int h, fftw_complex* in, const
 }
 void fftwf_execute(fftwf_plan pl) {
   PlanRec* p = reinterpret_cast<PlanRec*>(pl);
+  FftTimer timer;
   fft235_f32(static_cast<float*>(p->data), p->rank, p->n, p->howmany, p->dist, p->sign, g_threads);
 }
 void fftw_execute(fftw_plan pl) {
   PlanRec* p = reinterpret_cast<PlanRec*>(pl);
+  FftTimer timer;
   fft235_f64(static_cast<double*>(p->data), p->rank, p->n, p->howmany, p->dist, p->sign, g_threads);
+}
+// Stage timing for bench.py's cpu_baseline.stages_ms: seconds inside the FFT since the last call
+// with reset != 0 (the reference plan itself has no stage timers).
+double ref_fft_seconds(int reset) {
+  const double v = g_fft_seconds;
+  if (reset) g_fft_seconds = 0.0;
+  return v;
 }
 void fftwf_destroy_plan(fftwf_plan p) { delete reinterpret_cast<PlanRec*>(p); }
 void fftw_destroy_plan(fftw_plan p) { delete reinterpret_cast<PlanRec*>(p); }
