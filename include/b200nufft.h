@@ -19,7 +19,19 @@
  *   - all work is enqueued on the caller's stream; no device-wide synchronisation, except that
  *     set_points with check_points_range=1 reads one flag back (as the reference does,
  *     nufft_plan.h:880-898).
- * Handles are not thread-safe; distinct handles are independent.
+ * Memory: by default a plan allocates its buffers with cudaMalloc, growing geometrically when a
+ * larger point set arrives. Three ways to take that off the hot path / hand ownership to the host
+ * framework (TF's BFC allocator, nufft_plan.cu.cc:1981-2013 uses allocate_temp):
+ *   - b200nufft_reserve(plan, M): size every per-point buffer once; set_points with <= M points and
+ *     execute then never allocate or free;
+ *   - b200nufft_plan_create_ex with a b200nufft_allocator: every device allocation goes through the
+ *     caller's callbacks (long-lived raw allocations, e.g. tensorflow::Allocator::AllocateRaw);
+ *   - opts.external_workspace = 1 + b200nufft_workspace_bytes / b200nufft_bind_workspace: the caller
+ *     allocates ONE block (allocate_temp / torch.empty) per op call and the plan carves its fine
+ *     grid and per-point buffers out of it.
+ * Every entry point saves and restores the calling thread's current CUDA device. A handle may be
+ * used from several threads / streams: calls on one handle are serialised by a per-plan lock, and
+ * work enqueued on a new stream waits (cudaStreamWaitEvent) for the plan's previous work.
  */
 #ifndef B200NUFFT_H_
 #define B200NUFFT_H_
@@ -52,8 +64,9 @@ enum { B200NUFFT_RANGE_STRICT = 0, B200NUFFT_RANGE_EXTENDED = 1, B200NUFFT_RANGE
 typedef struct b200nufft_opts {
   int points_range;        /* B200NUFFT_RANGE_*; tfft.nufft sends EXTENDED (nufft_options.py:251) */
   int check_points_range;  /* options.debugging.check_points_range                               */
-  int max_batch_size;      /* options.max_batch_size; 0 = min(num_transforms, 8)
-                              (nufft_plan.cu.cc:1923-1928)                                        */
+  int max_batch_size;      /* options.max_batch_size; 0 = min(num_transforms, 32) with the fine-grid
+                              batch capped at 4 GiB (the reference: min(num_transforms, 8),
+                              nufft_plan.cu.cc:1923-1928); always clamped to 65535                */
   int spread_only;         /* Interp/Spread ops: no oversampling, no FFT, no deconvolution
                               (nufft_kernels.cc:457-460)                                          */
   int fseries_mode;        /* 0 = reference-compatible deconvolution factors: FloatType arithmetic
@@ -71,6 +84,15 @@ typedef struct b200nufft_opts {
                               lanes over one point's stencil, 3 shared-memory tiles, quarter warp
                               per point                                                           */
   int profile;             /* 1: record CUDA events around the stages (b200nufft_get_timings)     */
+  int upsampling;          /* fine-grid oversampling sigma: 0 = 2.0 (what Plan<GPUDevice> always uses,
+                              nufft_plan.cu.cc:1855-1857); 1 = 1.25 (low-upsampling mode, width and
+                              beta per nufft_plan.h:769-771 / nufft_plan.cu.cc:3089-3092); 2 = the
+                              reference CPU plan's automatic choice (nufft_plan.h:739-752)         */
+  int reuse_points;        /* 1: set_points fingerprints the raw coordinates on the device and, when
+                              they equal the previous call's, every set_points kernel exits at once
+                              (bin-sort and stencil records are kept). No host synchronisation.  */
+  int external_workspace;  /* 1: the plan allocates no fine grid / per-point buffers itself; the
+                              caller binds a block with b200nufft_bind_workspace                  */
   int reserved[8];         /* engine A/B switches used by the tests and probes (0 = default):
                               [0] 1: stage interpolator tiles with cp.async instead of TMA
                               [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8)
@@ -96,6 +118,16 @@ typedef struct b200nufft_info {
 
 void b200nufft_default_opts(b200nufft_opts* opts);
 
+/* Device-memory callbacks (e.g. thunks around tensorflow::Allocator::AllocateRaw/DeallocateRaw or
+ * torch's caching allocator). alloc returns a device pointer aligned to >= 256 bytes, or NULL. */
+typedef void* (*b200nufft_alloc_fn)(void* user, size_t bytes, int device);
+typedef void (*b200nufft_free_fn)(void* user, void* ptr, int device);
+typedef struct b200nufft_allocator {
+  b200nufft_alloc_fn alloc;
+  b200nufft_free_fn free;
+  void* user;
+} b200nufft_allocator;
+
 /* Replaces Plan<GPUDevice,F>::initialize (nufft_plan.cu.cc:1809-2030).
  * type 1|2; rank 1..3; fft_sign -1 forward / +1 backward (FftDirection, nufft_plan.h:126-129);
  * tol is the value the plan sees, i.e. static_cast<FloatType>(float attr) (nufft_kernels.cc:361);
@@ -105,8 +137,51 @@ int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_
                           int fft_sign, int num_transforms, double tol, int dtype,
                           const b200nufft_opts* opts, int device);
 
+/* Same, with every device allocation routed through `allocator` (NULL = cudaMalloc/cudaFree).
+ * Replaces the allocate_temp calls of Plan<GPUDevice,F>::initialize (nufft_plan.cu.cc:1981-2013). */
+int b200nufft_plan_create_ex(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims,
+                             int fft_sign, int num_transforms, double tol, int dtype,
+                             const b200nufft_opts* opts, int device,
+                             const b200nufft_allocator* allocator);
+
 /* Replaces ~Plan (nufft_plan.cu.cc:2032-2052). */
 void b200nufft_plan_destroy(b200nufft_plan* plan);
+
+/* Process-level plan cache (LRU; capacity from the environment variable B200NUFFT_PLAN_CACHE,
+ * default 8 idle plans), keyed by every create argument including opts and the allocator. The
+ * reference builds and tears down a plan (cuFFT plan, buffers, kernel factors) inside every op call
+ * (nufft_kernels.cc:475); with acquire / release the OpKernel keeps them across calls, and with
+ * opts.reuse_points = 1 also the bin-sort of an unchanged trajectory. acquire hands out an idle
+ * cached plan or creates one; a plan is never handed to two callers at once. release returns it
+ * (evicting, i.e. destroying, the least recently used idle plan beyond the capacity). */
+int b200nufft_plan_acquire(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims,
+                           int fft_sign, int num_transforms, double tol, int dtype,
+                           const b200nufft_opts* opts, int device,
+                           const b200nufft_allocator* allocator);
+void b200nufft_plan_release(b200nufft_plan* plan);
+void b200nufft_plan_cache_clear(void);
+/* out[0] = acquire calls served from the cache, out[1] = acquire calls that created a plan,
+ * out[2] = idle plans held now. */
+void b200nufft_plan_cache_stats(int64_t out[3]);
+
+/* Bytes of ONE caller-owned block that holds the fine-grid batch and every per-point buffer of this
+ * plan for point sets of up to num_points points (PlanBase's allocate_temp calls,
+ * nufft_plan.cu.cc:1981-2013, 2897-3032). */
+size_t b200nufft_workspace_bytes(const b200nufft_plan* plan, int64_t num_points);
+/* Carves the plan's buffers out of `workspace` (device memory, >= workspace_bytes(plan,
+ * num_points), 256-byte aligned). Until unbind, set_points (<= num_points points) and execute
+ * neither allocate nor free. Binding invalidates the current point set. */
+int b200nufft_bind_workspace(b200nufft_plan* plan, void* workspace, size_t bytes, int64_t num_points);
+int b200nufft_unbind_workspace(b200nufft_plan* plan);
+/* Sizes the plan's own per-point buffers for up to num_points points now, so that later
+ * set_points / execute calls never call the allocator. */
+int b200nufft_reserve(b200nufft_plan* plan, int64_t num_points);
+/* Number of device allocations / frees issued by this library so far in this process (cudaMalloc or
+ * allocator callbacks); lets a test assert that a code path does not allocate. */
+void b200nufft_debug_alloc_counts(int64_t* allocs, int64_t* frees);
+/* Test hook: out[0] = set_points calls on this plan that were skipped by the device-side
+ * fingerprint match (opts.reuse_points), out[1] = calls that did the full work. Synchronises. */
+int b200nufft_get_reuse_stats(b200nufft_plan* plan, int64_t out[2]);
 
 /* Replaces Plan<GPUDevice,F>::set_points (nufft_plan.cu.cc:2054-2111): range check (optional),
  * fold+rescale (nufft_plan.h:676-734, 901-948), bin-sort (:2897-2991), subproblem setup

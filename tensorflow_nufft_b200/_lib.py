@@ -27,8 +27,20 @@ class Opts(ctypes.Structure):
       ("spread_method", ctypes.c_int),
       ("interp_method", ctypes.c_int),
       ("profile", ctypes.c_int),
+      ("upsampling", ctypes.c_int),
+      ("reuse_points", ctypes.c_int),
+      ("external_workspace", ctypes.c_int),
       ("reserved", ctypes.c_int * 8),
   ]
+
+
+ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
+FREE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int)
+
+
+class Allocator(ctypes.Structure):
+  """b200nufft_allocator: device-memory callbacks (alloc, free, user)."""
+  _fields_ = [("alloc", ALLOC_FN), ("free", FREE_FN), ("user", ctypes.c_void_p)]
 
 
 class Info(ctypes.Structure):
@@ -69,7 +81,22 @@ SIGNATURES = [
     ("b200nufft_plan_create", ctypes.c_int,
      [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
       ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Opts), ctypes.c_int]),
+    ("b200nufft_plan_create_ex", ctypes.c_int,
+     [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+      ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Opts), ctypes.c_int, ctypes.POINTER(Allocator)]),
     ("b200nufft_plan_destroy", None, [_P]),
+    ("b200nufft_plan_acquire", ctypes.c_int,
+     [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+      ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Opts), ctypes.c_int, ctypes.POINTER(Allocator)]),
+    ("b200nufft_plan_release", None, [_P]),
+    ("b200nufft_plan_cache_clear", None, []),
+    ("b200nufft_plan_cache_stats", None, [ctypes.POINTER(ctypes.c_int64)]),
+    ("b200nufft_workspace_bytes", ctypes.c_size_t, [_P, ctypes.c_int64]),
+    ("b200nufft_bind_workspace", ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.c_int64]),
+    ("b200nufft_unbind_workspace", ctypes.c_int, [_P]),
+    ("b200nufft_reserve", ctypes.c_int, [_P, ctypes.c_int64]),
+    ("b200nufft_debug_alloc_counts", None, [ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    ("b200nufft_get_reuse_stats", ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
     ("b200nufft_set_points", ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P, _P]),
     ("b200nufft_set_points_interleaved", ctypes.c_int, [_P, ctypes.c_int64, _P, _P]),
     ("b200nufft_execute", ctypes.c_int, [_P, _P, _P, _P]),
@@ -129,49 +156,76 @@ def raise_for(code, message):
   raise NufftError(code, "Internal: " + message)
 
 
+def make_opts(**opt_kwargs):
+  """b200nufft_opts from keyword arguments (field names of the C struct, plus names for the
+  reserved[] A/B switches)."""
+  opts = Opts()
+  lib().b200nufft_default_opts(ctypes.byref(opts))
+  reserved = {"no_tma": 0, "coils_per_cta": 1, "kernel_variant": 2, "full_fft": 4, "no_tma_flush": 5,
+              "no_zrange": 6}
+  for k, v in opt_kwargs.items():
+    if k == "bin_dims":
+      for i, b in enumerate(v):
+        opts.bin_dims[i] = int(b)
+    elif k in reserved:
+      opts.reserved[reserved[k]] = int(v)
+    else:
+      if not hasattr(opts, k):
+        raise TypeError(f"unknown option {k}")
+      setattr(opts, k, int(v))
+  return opts
+
+
+def alloc_counts():
+  """(allocations, frees) issued by the library so far (cudaMalloc or allocator callbacks)."""
+  a, f = ctypes.c_int64(), ctypes.c_int64()
+  lib().b200nufft_debug_alloc_counts(ctypes.byref(a), ctypes.byref(f))
+  return a.value, f.value
+
+
+def plan_cache_stats():
+  out = (ctypes.c_int64 * 3)()
+  lib().b200nufft_plan_cache_stats(out)
+  return {"hits": out[0], "misses": out[1], "idle": out[2]}
+
+
+def plan_cache_clear():
+  lib().b200nufft_plan_cache_clear()
+
+
 class Plan:
-  """Owns one b200nufft_plan handle. Pointers are raw device addresses (ints)."""
+  """Owns one b200nufft_plan handle. Pointers are raw device addresses (ints).
+
+  cached=True takes the handle from the library's process-level plan cache
+  (b200nufft_plan_acquire) and close() gives it back (b200nufft_plan_release) instead of
+  destroying it. allocator: an `Allocator` (kept alive by this object)."""
 
   def __init__(self, transform_type, grid_dims, fft_sign, num_transforms, tol, dtype_code,
-               device=0, **opt_kwargs):
+               device=0, cached=False, allocator=None, **opt_kwargs):
     L = lib()
-    opts = Opts()
-    L.b200nufft_default_opts(ctypes.byref(opts))
-    for k, v in opt_kwargs.items():
-      if k == "bin_dims":
-        for i, b in enumerate(v):
-          opts.bin_dims[i] = int(b)
-      elif k == "no_tma":
-        opts.reserved[0] = int(v)
-      elif k == "coils_per_cta":
-        opts.reserved[1] = int(v)
-      elif k == "kernel_variant":
-        opts.reserved[2] = int(v)
-      elif k == "full_fft":
-        opts.reserved[4] = int(v)
-      elif k == "no_zrange":
-        opts.reserved[6] = int(v)
-      elif k == "no_tma_flush":
-        opts.reserved[5] = int(v)
-      else:
-        if not hasattr(opts, k):
-          raise TypeError(f"unknown option {k}")
-        setattr(opts, k, int(v))
+    opts = make_opts(**opt_kwargs)
     self.rank = len(grid_dims)
     gd = (ctypes.c_int64 * 3)(*([int(g) for g in grid_dims] + [1] * (3 - self.rank)))
     h = _P()
-    rc = L.b200nufft_plan_create(ctypes.byref(h), int(transform_type), self.rank, gd, int(fft_sign),
-                                 int(num_transforms), float(tol), int(dtype_code),
-                                 ctypes.byref(opts), int(device))
+    self._allocator = allocator
+    aptr = ctypes.byref(allocator) if allocator is not None else None
+    args = (ctypes.byref(h), int(transform_type), self.rank, gd, int(fft_sign), int(num_transforms),
+            float(tol), int(dtype_code), ctypes.byref(opts), int(device))
+    if cached:
+      rc = L.b200nufft_plan_acquire(*args, aptr)
+    elif allocator is not None:
+      rc = L.b200nufft_plan_create_ex(*args, aptr)
+    else:
+      rc = L.b200nufft_plan_create(*args)
     if rc != OK:
       raise_for(rc, L.b200nufft_last_create_error().decode())
     self._h = h
+    self.cached = bool(cached)
     self.type = int(transform_type)
     self.num_transforms = int(num_transforms)
     self.grid_dims = [int(g) for g in grid_dims]
     self.dtype_code = int(dtype_code)
     self.device = int(device)
-    self.points_token = None
 
   def _check(self, rc):
     if rc != OK:
@@ -232,9 +286,29 @@ class Plan:
   def launch_count(self):
     return int(lib().b200nufft_launch_count(self._h))
 
+  def workspace_bytes(self, num_points):
+    return int(lib().b200nufft_workspace_bytes(self._h, int(num_points)))
+
+  def bind_workspace(self, ptr, nbytes, num_points):
+    self._check(lib().b200nufft_bind_workspace(self._h, ptr, int(nbytes), int(num_points)))
+
+  def unbind_workspace(self):
+    self._check(lib().b200nufft_unbind_workspace(self._h))
+
+  def reserve(self, num_points):
+    self._check(lib().b200nufft_reserve(self._h, int(num_points)))
+
+  def reuse_stats(self):
+    out = (ctypes.c_int64 * 2)()
+    self._check(lib().b200nufft_get_reuse_stats(self._h, out))
+    return {"skipped": out[0], "full": out[1]}
+
   def close(self):
     if getattr(self, "_h", None):
-      lib().b200nufft_plan_destroy(self._h)
+      if self.cached:
+        lib().b200nufft_plan_release(self._h)
+      else:
+        lib().b200nufft_plan_destroy(self._h)
       self._h = None
 
   def __del__(self):

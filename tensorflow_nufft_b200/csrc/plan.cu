@@ -8,10 +8,14 @@
 #include <cufft.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <list>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -35,23 +39,66 @@ namespace {
 
 thread_local std::string g_create_error;
 
+std::atomic<int64_t> g_allocs{0}, g_frees{0};
+
+// Saves / restores the calling thread's current device around an entry point (a plan on another
+// device must not leave the caller on that device).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) { cudaSetDevice(dev); changed = true; }
+  }
+  ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+};
+
+// Where a plan's device memory comes from: cudaMalloc/cudaFree, or the caller's callbacks.
+struct MemCtx {
+  b200nufft_allocator a{nullptr, nullptr, nullptr};
+  int device = 0;
+  cudaError_t alloc(void** p, size_t bytes) {
+    g_allocs++;
+    if (a.alloc) {
+      *p = a.alloc(a.user, bytes, device);
+      return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+    }
+    return cudaMalloc(p, bytes);
+  }
+  void free(void* p) {
+    if (!p) return;
+    g_frees++;
+    if (a.free) a.free(a.user, p, device);
+    else cudaFree(p);
+  }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
+  bool external = false;   // carved out of a caller-owned workspace: never freed here
+  // headroom: grow by 1/8 more than asked, so that slowly growing point sets do not reallocate
+  cudaError_t reserve(MemCtx& m, size_t bytes, bool headroom = true) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
+    if (external) return cudaErrorMemoryAllocation;   // a bound workspace is never outgrown silently
+    release(m);
+    size_t want = headroom ? bytes + bytes / 8 + 256 : bytes;
+    want = (want + 255) & ~static_cast<size_t>(255);
+    cudaError_t e = m.alloc(&p, want);
     if (e == cudaSuccess) cap = want;
+    else p = nullptr;
     return e;
   }
-  void release() {
-    if (p) cudaFree(p);
+  void release(MemCtx& m) {
+    if (p && !external) m.free(p);
     p = nullptr;
     cap = 0;
+    external = false;
+  }
+  void bind(void* ptr, size_t bytes) {
+    p = ptr;
+    cap = bytes;
+    external = true;
   }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -112,6 +159,23 @@ struct b200nufft_plan {
   bool points_set = false;
   DevBuf folded, keys0, keys1, vals0, vals1, hist, start, wrec;
   DevBuf bin_sizes, bin_start, num_sub, sub_start, sub_desc, misc;  // misc: scan tmp[1024] + sub_total + range flag
+  DevBuf reuse;            // ReuseState (opts.reuse_points)
+  MemCtx mem;
+  int nb_max = 1;          // largest bin count over the geometries set_points may choose
+  bool ws_bound = false;   // external workspace bound (opts.external_workspace)
+  int64_t ws_points = 0;   // ... for this many points
+  // point-set reuse: host-side knowledge of what the device-side fingerprint describes
+  bool fp_valid = false;
+  int64_t fp_M = -1;
+  int fp_layout = -1;
+  // cross-stream / cross-thread use of one handle
+  std::mutex mu;
+  cudaEvent_t done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_work = false;
+  // plan cache bookkeeping (b200nufft_plan_acquire / _release)
+  bool from_cache = false;
+  std::string cache_key;
   int* idx = nullptr;      // points at vals0 or vals1
   int64_t sub_bound = 0;
   int* h_flag = nullptr;   // pinned
@@ -127,6 +191,14 @@ struct b200nufft_plan {
   int* sub_total() const { return misc.as<int>() + kScanMaxBlocks; }
   // the range-check flag lives right behind the bin histogram so that one memset clears both
   int* range_flag() const { return bin_sizes.as<int>() + nbtot; }
+  ReuseState* reuse_state() const { return reuse.as<ReuseState>(); }
+  // skip flag read by every set_points kernel (nullptr: reuse off)
+  const int* skip_flag() const { return opts.reuse_points ? &reuse.as<ReuseState>()->skip : nullptr; }
+  // buffers that live in the caller's workspace when one is bound
+  std::vector<DevBuf*> ws_bufs() {
+    return {&fine, &bin_sizes, &bin_start, &num_sub, &sub_start, &folded, &keys0, &keys1, &vals0, &vals1,
+            &hist, &start, &wrec, &sub_desc};
+  }
 };
 
 namespace {
@@ -194,6 +266,47 @@ void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
   *hi = ub;
   *lo = -ub;
 }
+
+constexpr int kNumWsBufs = 14;
+// Bytes of every workspace-class buffer for point sets of up to M points, in ws_bufs() order.
+template <typename F>
+void ws_sizes(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
+  const int64_t m = std::max<int64_t>(M, 0);
+  const size_t bins = sizeof(int) * (static_cast<size_t>(p->nb_max) + 1);
+  const int msub_min = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 64;
+  const int64_t sub_bound = std::min<int64_t>(p->nb_max, m) + m / msub_min + 2;
+  out[0] = p->opts.spread_only ? 0 : sizeof(Cplx<F>) * static_cast<size_t>(p->nftot) * p->batch;
+  out[1] = out[2] = out[3] = out[4] = bins;
+  out[5] = sizeof(F) * 4 * m;
+  out[6] = out[7] = sizeof(uint32_t) * m;
+  out[8] = out[9] = sizeof(int) * m;
+  out[10] = sizeof(int) * radix_hist_ints(m);
+  out[11] = sizeof(int4) * m;
+  out[12] = sizeof(F) * m * p->R;
+  out[13] = sizeof(int4) * sub_bound;
+}
+void ws_sizes_any(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
+  if (p->is_double) ws_sizes<double>(p, M, out); else ws_sizes<float>(p, M, out);
+}
+inline size_t align256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+
+// Serialises the calls on one handle and orders its work across streams: a call on a new stream
+// first waits for the event recorded after the plan's previous call.
+struct PlanCall {
+  b200nufft_plan* p;
+  std::lock_guard<std::mutex> lock;
+  DeviceGuard dev;
+  cudaStream_t st;
+  PlanCall(b200nufft_plan* plan, cudaStream_t stream) : p(plan), lock(plan->mu), dev(plan->device), st(stream) {
+    if (p->has_work && p->done && st != p->last_stream) cudaStreamWaitEvent(st, p->done, 0);
+  }
+  ~PlanCall() {
+    if (p->done && cudaEventRecord(p->done, st) == cudaSuccess) {
+      p->has_work = true;
+      p->last_stream = st;
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // Tile-kernel dispatch on the kernel width.
@@ -660,18 +773,42 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
       p->nbtot = p->nbins[0] * p->nbins[1] * p->nbins[2];
     }
   }
-  CUDA_OK(p, p->bin_sizes.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->bin_start.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->num_sub.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->sub_start.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->folded.reserve(sizeof(F) * 4 * M));
-  CUDA_OK(p, p->keys0.reserve(sizeof(uint32_t) * M));
-  CUDA_OK(p, p->keys1.reserve(sizeof(uint32_t) * M));
-  CUDA_OK(p, p->vals0.reserve(sizeof(int) * M));
-  CUDA_OK(p, p->vals1.reserve(sizeof(int) * M));
-  CUDA_OK(p, p->hist.reserve(sizeof(int) * radix_hist_ints(M)));
-  CUDA_OK(p, p->start.reserve(sizeof(int4) * M));
-  CUDA_OK(p, p->wrec.reserve(sizeof(F) * M * p->R));
+  // Buffers: a bound workspace must already hold M points; otherwise grow the plan's own buffers
+  // (geometric headroom; b200nufft_reserve sizes them ahead of time so that this never allocates).
+  if (p->ws_bound) {
+    if (M > p->ws_points)
+      return set_err(p, B200NUFFT_RESOURCE_EXHAUSTED, "workspace was bound for %lld points, set_points got %lld",
+                     (long long)p->ws_points, (long long)M);
+  } else if (p->opts.external_workspace) {
+    return set_err(p, B200NUFFT_INVALID_ARGUMENT, "external_workspace plan: call b200nufft_bind_workspace first");
+  } else {
+    size_t need[kNumWsBufs];
+    ws_sizes<F>(p, M, need);
+    auto bufs = p->ws_bufs();
+    for (int i = 1; i < kNumWsBufs; ++i) {
+      if (need[i] > bufs[i]->cap) p->fp_valid = false;   // contents are lost with the old buffer
+      CUDA_OK(p, bufs[i]->reserve(p->mem, need[i]));
+    }
+  }
+
+  // Point-set reuse: fingerprint the raw coordinates; on a match with the set the buffers hold,
+  // the kernels below exit at once (skip flag), all on the stream, no host round trip.
+  const int* skip = p->skip_flag();
+  if (skip) {
+    const int allow = (p->fp_valid && p->fp_M == M && p->fp_layout == layout) ? 1 : 0;
+    const int64_t wpr = sizeof(F) / 4;   // 32-bit words per real
+    const int64_t n0 = (layout == 1 ? M * rank : M) * wpr;
+    const int64_t n1 = (layout == 0 && rank > 1) ? M * wpr : 0;
+    const int64_t n2 = (layout == 0 && rank > 2) ? M * wpr : 0;
+    fingerprint_kernel<<<grid_for(n0 + n1 + n2, 256 * 4, 4), 256, 0, st>>>(
+        static_cast<const uint32_t*>(x), n0, static_cast<const uint32_t*>(y), n1,
+        static_cast<const uint32_t*>(z), n2, allow, p->reuse_state());
+    LAUNCH_OK(p);
+    p->launches++;
+    p->fp_valid = true;
+    p->fp_M = M;
+    p->fp_layout = layout;
+  }
 
   BinGeom bg;
   bg.rank = rank;
@@ -684,7 +821,12 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.align_y = p->ws2 ? 1 : 0;
   const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY : 1);
 
-  CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * (p->nbtot + 1), st));   // histogram + range flag
+  if (skip) {
+    clear_ints_kernel<<<grid_for(p->nbtot + 1, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot + 1, skip);
+    p->launches++;
+  } else {
+    CUDA_OK(p, cudaMemsetAsync(p->bin_sizes.p, 0, sizeof(int) * (p->nbtot + 1), st));   // histogram + range flag
+  }
   F lo, hi;
   points_bounds<F>(p, &lo, &hi);
   const int check = p->opts.check_points_range && p->opts.points_range != B200NUFFT_RANGE_INFINITE;
@@ -692,7 +834,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
       M, layout, static_cast<const F*>(x), static_cast<const F*>(y), static_cast<const F*>(z),
       p->opts.points_range, check, lo, hi, bg, static_cast<F>(p->kp.half_width), p->folded.as<F>(),
       p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
-      p->range_flag());
+      p->range_flag(), skip);
   LAUNCH_OK(p);
   p->launches++;
 
@@ -700,7 +842,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   int* vs;
   p->launches += radix_sort_pairs(p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->keys1.as<uint32_t>(),
                                   p->vals1.as<int>(), M, ilog2_ceil(key_space), p->hist.as<int>(),
-                                  p->scan_tmp(), &ks, &vs, st);
+                                  p->scan_tmp(), &ks, &vs, st, skip);
   LAUNCH_OK(p);
   p->idx = vs;
 
@@ -717,22 +859,21 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   // No host read of the subproblem count (the reference blocks on it, nufft_plan.cu.cc:3011):
   // launch the bound, surplus CTAs exit on the device-side count.
   p->sub_bound = std::min<int64_t>(p->nbtot, M) + M / p->msub;
-  CUDA_OK(p, p->sub_desc.reserve(sizeof(int4) * (p->sub_bound + 1)));
   if (p->nbtot <= kScanSmallMax) {
     bins_small_kernel<<<1, 1024, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub, p->bin_start.as<int>(),
-                                         p->sub_start.as<int>(), p->sub_total(), p->sub_desc.as<int4>());
+                                         p->sub_start.as<int>(), p->sub_total(), p->sub_desc.as<int4>(), skip);
     p->launches++;
   } else {
     p->launches += exclusive_scan_i32(p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->nbtot,
-                                      p->scan_tmp(), nullptr, st);
+                                      p->scan_tmp(), nullptr, st, skip);
     subproblem_count_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot, p->msub,
-                                                                    p->num_sub.as<int>());
+                                                                    p->num_sub.as<int>(), skip);
     p->launches++;
     p->launches += exclusive_scan_i32(p->num_sub.as<int>(), p->sub_start.as<int>(), p->nbtot, p->scan_tmp(),
-                                      p->sub_total(), st);
+                                      p->sub_total(), st, skip);
     subproblem_desc_kernel<<<ceil_div(p->nbtot, 256), 256, 0, st>>>(
         p->bin_sizes.as<int>(), p->bin_start.as<int>(), p->sub_start.as<int>(), p->nbtot, p->msub,
-        p->sub_desc.as<int4>());
+        p->sub_desc.as<int4>(), skip);
     p->launches++;
   }
   LAUNCH_OK(p);
@@ -744,16 +885,16 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     if (rank == 2)
       stencil_record8_kernel<F, 2><<<grid_for(M * 2, 256, 16), 256, 0, st>>>(
           M, p->idx, p->folded.as<F>(), p->kp.ns, beta, cc, hw,
-          align, p->start.as<int>(), p->wrec.as<F>());
+          align, p->start.as<int>(), p->wrec.as<F>(), skip);
     else
       stencil_record8_kernel<F, 3><<<grid_for(M * 3, 256, 16), 256, 0, st>>>(
           M, p->idx, p->folded.as<F>(), p->kp.ns, beta, cc, hw,
-          align_x, p->start.as<int>(), p->wrec.as<F>());
+          align_x, p->start.as<int>(), p->wrec.as<F>(), skip);
   } else {
     stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
         M, rank, p->idx, p->folded.as<F>(), p->kp.ns,
         static_cast<F>(p->kp.beta), static_cast<F>(p->kp.c), static_cast<F>(p->kp.half_width), align_x,
-        p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>());
+        p->R, p->PX, p->PY, p->start.as<int4>(), p->wrec.as<F>(), skip);
   }
   LAUNCH_OK(p);
   p->launches++;
@@ -763,7 +904,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   const bool zr_spread = p->spread_method == 2 && (p->type == 1 || p->opts.spread_only);
   if (rank == 3 && !p->is_double && (zr_interp || zr_spread) && p->sub_bound > 0) {
     subproblem_zrange_kernel<<<ceil_div(p->sub_bound, 8), 256, 0, st>>>(p->sub_total(), p->start.as<int4>(),
-                                                                       p->sub_desc.as<int4>());
+                                                                       p->sub_desc.as<int4>(), skip);
     LAUNCH_OK(p);
     p->launches++;
     p->zrange_valid = true;
@@ -810,6 +951,7 @@ int create_impl(b200nufft_plan* p) {
     const int cap = static_cast<int>(std::max<int64_t>(1, (int64_t(4) << 30) / std::max<int64_t>(1, grid_bytes)));
     p->batch = p->opts.max_batch_size > 0 ? std::min(p->opts.max_batch_size, p->ntransf)
                                           : std::min(std::min(p->ntransf, 32), cap);
+    p->batch = std::max(1, std::min(p->batch, 65535));   // the batch is a grid dimension of every launch
   }
   if (p->nftot * p->batch > 2000000000LL) {
     // shrink the batch rather than fail (the reference errors out above kMaxArraySize elements)
@@ -872,6 +1014,10 @@ int create_impl(b200nufft_plan* p) {
   }
   p->adaptive_bin_z = p->rank == 3 && p->type == 2 && !p->opts.spread_only && tile_ok && p->interp_method == 3 &&
                       p->opts.bin_dims[2] == 0 && p->bin[0] == 16 && p->bin[1] == 8;
+  p->nb_max = p->nbtot;
+  if (p->adaptive_bin_z) {   // set_points picks a bin depth of 2 or 8
+    for (int bz : {2, 8}) p->nb_max = std::max(p->nb_max, p->nbins[0] * p->nbins[1] * ((p->nf[2] + bz - 1) / bz));
+  }
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && ws_any;
@@ -916,10 +1062,11 @@ int create_impl(b200nufft_plan* p) {
       p->fser_host[d].resize(sizeof(F) * nc);
       kernel_fseries<F>(p->nf[d], p->kp, p->opts.fseries_mode, p->num_threads_compat,
                         reinterpret_cast<F*>(p->fser_host[d].data()));
-      CUDA_OK(p, p->fser[d].reserve(sizeof(F) * nc));
+      CUDA_OK(p, p->fser[d].reserve(p->mem, sizeof(F) * nc, false));
       CUDA_OK(p, cudaMemcpy(p->fser[d].p, p->fser_host[d].data(), sizeof(F) * nc, cudaMemcpyHostToDevice));
     }
-    CUDA_OK(p, p->fine.reserve(sizeof(Cplx<F>) * p->nftot * p->batch));
+    if (!p->opts.external_workspace)
+      CUDA_OK(p, p->fine.reserve(p->mem, sizeof(Cplx<F>) * p->nftot * p->batch, false));
     const cufftType ftype = p->is_double ? CUFFT_Z2Z : CUFFT_C2C;
     if (p->rank == 3 && p->opts.reserved[4] == 0) {
       // modes k = -(n/2) .. (n-1)/2 live in fine planes [0, zlo) and [nf - zhi, nf)
@@ -952,11 +1099,16 @@ int create_impl(b200nufft_plan* p) {
       p->has_fft = true;
     }
   }
-  CUDA_OK(p, p->bin_sizes.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->bin_start.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->num_sub.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->sub_start.reserve(sizeof(int) * (p->nbtot + 1)));
-  CUDA_OK(p, p->misc.reserve(sizeof(int) * (kScanMaxBlocks + 8)));
+  if (!p->opts.external_workspace) {
+    for (DevBuf* b : {&p->bin_sizes, &p->bin_start, &p->num_sub, &p->sub_start})
+      CUDA_OK(p, b->reserve(p->mem, sizeof(int) * (static_cast<size_t>(p->nb_max) + 1), false));
+  }
+  CUDA_OK(p, p->misc.reserve(p->mem, sizeof(int) * (kScanMaxBlocks + 8), false));
+  if (p->opts.reuse_points) {
+    CUDA_OK(p, p->reuse.reserve(p->mem, sizeof(ReuseState), false));
+    CUDA_OK(p, cudaMemset(p->reuse.p, 0, sizeof(ReuseState)));
+  }
+  CUDA_OK(p, cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
   CUDA_OK(p, cudaMallocHost(&p->h_flag, sizeof(int)));
   if (p->opts.profile) {
     CUDA_OK(p, cudaEventCreate(&p->ev[4]));
@@ -977,8 +1129,10 @@ void b200nufft_default_opts(b200nufft_opts* o) {
   o->points_range = B200NUFFT_RANGE_EXTENDED;
 }
 
-int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
-                          int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device) {
+namespace {
+int plan_create_common(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
+                       int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device,
+                       const b200nufft_allocator* allocator) {
   if (!out) return B200NUFFT_INVALID_ARGUMENT;
   *out = nullptr;
   auto fail = [&](int code, const std::string& m) { g_create_error = m; return code; };
@@ -987,18 +1141,21 @@ int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_
   if (num_transforms < 1) return fail(B200NUFFT_INVALID_ARGUMENT, "num_transforms must be >= 1");
   if (dtype != B200NUFFT_COMPLEX64 && dtype != B200NUFFT_COMPLEX128) return fail(B200NUFFT_INVALID_ARGUMENT, "invalid dtype");
   if (fft_sign != 1 && fft_sign != -1) return fail(B200NUFFT_INVALID_ARGUMENT, "fft_sign must be -1 or +1");
+  if (allocator && (!allocator->alloc || !allocator->free))
+    return fail(B200NUFFT_INVALID_ARGUMENT, "allocator needs both alloc and free callbacks");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
     return fail(B200NUFFT_INTERNAL, std::string("no CUDA device available: ") + cudaGetErrorString(ce) +
                                         " (this engine has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail(B200NUFFT_INVALID_ARGUMENT, "invalid device ordinal");
-  ce = cudaSetDevice(device);
-  if (ce != cudaSuccess) return fail(B200NUFFT_INTERNAL, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+  DeviceGuard guard(device);
 
   b200nufft_plan* p = new b200nufft_plan();
   p->type = type; p->rank = rank; p->fft_sign = fft_sign; p->ntransf = num_transforms;
   p->dtype = dtype; p->is_double = dtype == B200NUFFT_COMPLEX128; p->device = device; p->tol = tol;
+  p->mem.device = device;
+  if (allocator) p->mem.a = *allocator;
   if (opts) p->opts = *opts; else b200nufft_default_opts(&p->opts);
   p->n_modes_tot = 1;
   for (int d = 0; d < rank; ++d) {
@@ -1019,35 +1176,229 @@ int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_
   return B200NUFFT_OK;
 }
 
+// ---- process-level plan cache -------------------------------------------------------------------
+struct PlanCache {
+  std::mutex mu;
+  std::list<b200nufft_plan*> idle;   // most recently released first
+  int64_t hits = 0, misses = 0;
+  size_t capacity = 8;
+  PlanCache() {
+    if (const char* e = std::getenv("B200NUFFT_PLAN_CACHE")) capacity = static_cast<size_t>(std::max(0, std::atoi(e)));
+  }
+};
+PlanCache& plan_cache() {
+  static PlanCache* c = new PlanCache();   // never destroyed: plans must not outlive the CUDA context teardown order
+  return *c;
+}
+std::string make_cache_key(int type, int rank, const int64_t* grid_dims, int fft_sign, int num_transforms, double tol,
+                           int dtype, const b200nufft_opts* opts, int device, const b200nufft_allocator* allocator) {
+  b200nufft_opts o;
+  if (opts) o = *opts; else b200nufft_default_opts(&o);
+  std::string k;
+  auto put = [&k](const void* ptr, size_t n) { k.append(static_cast<const char*>(ptr), n); };
+  int64_t dims[3] = {1, 1, 1};
+  for (int d = 0; d < rank && d < 3; ++d) dims[d] = grid_dims[d];
+  put(&type, sizeof type); put(&rank, sizeof rank); put(dims, sizeof dims); put(&fft_sign, sizeof fft_sign);
+  put(&num_transforms, sizeof num_transforms); put(&tol, sizeof tol); put(&dtype, sizeof dtype);
+  put(&o, sizeof o); put(&device, sizeof device);
+  b200nufft_allocator a{nullptr, nullptr, nullptr};
+  if (allocator) a = *allocator;
+  put(&a.alloc, sizeof a.alloc); put(&a.free, sizeof a.free); put(&a.user, sizeof a.user);
+  return k;
+}
+}  // namespace
+
+int b200nufft_plan_create(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
+                          int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device) {
+  return plan_create_common(out, type, rank, grid_dims, fft_sign, num_transforms, tol, dtype, opts, device, nullptr);
+}
+
+int b200nufft_plan_create_ex(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
+                             int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device,
+                             const b200nufft_allocator* allocator) {
+  return plan_create_common(out, type, rank, grid_dims, fft_sign, num_transforms, tol, dtype, opts, device, allocator);
+}
+
 void b200nufft_plan_destroy(b200nufft_plan* p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  DeviceGuard guard(p->device);
   if (p->has_fft) cufftDestroy(p->fft);
   if (p->has_fft_rem) cufftDestroy(p->fft_rem);
   if (p->fft_xy_lo) cufftDestroy(p->fft_xy_lo);
   if (p->fft_xy_hi) cufftDestroy(p->fft_xy_hi);
   if (p->fft_z) cufftDestroy(p->fft_z);
-  p->fine.release();
-  for (int d = 0; d < 3; ++d) p->fser[d].release();
-  p->folded.release();
-  p->keys0.release(); p->keys1.release(); p->vals0.release(); p->vals1.release(); p->hist.release();
-  p->start.release(); p->wrec.release(); p->bin_sizes.release(); p->bin_start.release();
-  p->num_sub.release(); p->sub_start.release(); p->sub_desc.release(); p->misc.release();
+  for (DevBuf* b : p->ws_bufs()) b->release(p->mem);
+  for (int d = 0; d < 3; ++d) p->fser[d].release(p->mem);
+  p->misc.release(p->mem);
+  p->reuse.release(p->mem);
   if (p->h_flag) cudaFreeHost(p->h_flag);
+  if (p->done) cudaEventDestroy(p->done);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& e : p->ev_batch) cudaEventDestroy(e);
   delete p;
 }
 
+int b200nufft_plan_acquire(b200nufft_plan** out, int type, int rank, const int64_t* grid_dims, int fft_sign,
+                           int num_transforms, double tol, int dtype, const b200nufft_opts* opts, int device,
+                           const b200nufft_allocator* allocator) {
+  if (!out) return B200NUFFT_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (rank < 1 || rank > 3 || !grid_dims)   // let create produce the proper message
+    return plan_create_common(out, type, rank, grid_dims, fft_sign, num_transforms, tol, dtype, opts, device, allocator);
+  const std::string key = make_cache_key(type, rank, grid_dims, fft_sign, num_transforms, tol, dtype, opts, device, allocator);
+  PlanCache& c = plan_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (auto it = c.idle.begin(); it != c.idle.end(); ++it) {
+      if ((*it)->cache_key == key) {
+        *out = *it;
+        c.idle.erase(it);
+        c.hits++;
+        return B200NUFFT_OK;
+      }
+    }
+    c.misses++;
+  }
+  int rc = plan_create_common(out, type, rank, grid_dims, fft_sign, num_transforms, tol, dtype, opts, device, allocator);
+  if (rc == B200NUFFT_OK) {
+    (*out)->from_cache = true;
+    (*out)->cache_key = key;
+  }
+  return rc;
+}
+
+void b200nufft_plan_release(b200nufft_plan* p) {
+  if (!p) return;
+  if (!p->from_cache || p->ws_bound) {   // a plan still tied to a caller-owned block is not kept
+    if (p->ws_bound) b200nufft_unbind_workspace(p);
+    if (!p->from_cache) { b200nufft_plan_destroy(p); return; }
+  }
+  std::vector<b200nufft_plan*> evict;
+  PlanCache& c = plan_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.idle.push_front(p);
+    while (c.idle.size() > c.capacity) {
+      evict.push_back(c.idle.back());
+      c.idle.pop_back();
+    }
+  }
+  for (b200nufft_plan* e : evict) b200nufft_plan_destroy(e);
+}
+
+void b200nufft_plan_cache_clear(void) {
+  std::vector<b200nufft_plan*> all;
+  PlanCache& c = plan_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    all.assign(c.idle.begin(), c.idle.end());
+    c.idle.clear();
+  }
+  for (b200nufft_plan* e : all) b200nufft_plan_destroy(e);
+}
+
+void b200nufft_plan_cache_stats(int64_t out[3]) {
+  PlanCache& c = plan_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  out[0] = c.hits;
+  out[1] = c.misses;
+  out[2] = static_cast<int64_t>(c.idle.size());
+}
+
+size_t b200nufft_workspace_bytes(const b200nufft_plan* p, int64_t M) {
+  if (!p || M < 0) return 0;
+  size_t need[kNumWsBufs], total = 0;
+  ws_sizes_any(p, M, need);
+  for (int i = 0; i < kNumWsBufs; ++i) total += align256(need[i]);
+  return total + 256;
+}
+
+int b200nufft_bind_workspace(b200nufft_plan* p, void* workspace, size_t bytes, int64_t M) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (!workspace || M < 0) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bind_workspace: null workspace or negative num_points");
+  const size_t want = b200nufft_workspace_bytes(p, M);
+  if (bytes < want)
+    return set_err(p, B200NUFFT_RESOURCE_EXHAUSTED, "workspace of %zu bytes is too small: %zu needed for %lld points",
+                   bytes, want, (long long)M);
+  DeviceGuard guard(p->device);
+  size_t need[kNumWsBufs];
+  ws_sizes_any(p, M, need);
+  char* cur = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  auto bufs = p->ws_bufs();
+  for (int i = 0; i < kNumWsBufs; ++i) {
+    bufs[i]->release(p->mem);   // plan-owned buffers of this class are given back
+    bufs[i]->bind(cur, align256(need[i]));
+    cur += align256(need[i]);
+  }
+  p->ws_bound = true;
+  p->ws_points = M;
+  p->points_set = false;
+  p->fp_valid = false;
+  p->tmap_in.ok = p->tmap_out.ok = false;
+  return B200NUFFT_OK;
+}
+
+int b200nufft_unbind_workspace(b200nufft_plan* p) {
+  if (!p) return B200NUFFT_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (!p->ws_bound) return B200NUFFT_OK;
+  for (DevBuf* b : p->ws_bufs()) b->release(p->mem);   // external: pointers dropped, nothing freed
+  p->ws_bound = false;
+  p->ws_points = 0;
+  p->points_set = false;
+  p->fp_valid = false;
+  p->idx = nullptr;
+  p->tmap_in.ok = p->tmap_out.ok = false;
+  return B200NUFFT_OK;
+}
+
+int b200nufft_reserve(b200nufft_plan* p, int64_t M) {
+  if (!p || M < 0) return B200NUFFT_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->ws_bound || p->opts.external_workspace)
+    return set_err(p, B200NUFFT_INVALID_ARGUMENT, "reserve: this plan takes its buffers from a caller workspace");
+  DeviceGuard guard(p->device);
+  size_t need[kNumWsBufs];
+  ws_sizes_any(p, M, need);
+  auto bufs = p->ws_bufs();
+  for (int i = 1; i < kNumWsBufs; ++i) {
+    if (need[i] > bufs[i]->cap) { p->fp_valid = false; p->points_set = false; }
+    CUDA_OK(p, bufs[i]->reserve(p->mem, need[i], false));
+  }
+  return B200NUFFT_OK;
+}
+
+void b200nufft_debug_alloc_counts(int64_t* allocs, int64_t* frees) {
+  if (allocs) *allocs = g_allocs.load();
+  if (frees) *frees = g_frees.load();
+}
+
+int b200nufft_get_reuse_stats(b200nufft_plan* p, int64_t out[2]) {
+  if (!p || !out) return B200NUFFT_INVALID_ARGUMENT;
+  out[0] = out[1] = 0;
+  if (!p->opts.reuse_points) return B200NUFFT_OK;
+  std::lock_guard<std::mutex> lock(p->mu);
+  DeviceGuard guard(p->device);
+  ReuseState h;
+  CUDA_OK(p, cudaDeviceSynchronize());
+  CUDA_OK(p, cudaMemcpy(&h, p->reuse.p, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = h.n_skipped;
+  out[1] = h.n_full;
+  return B200NUFFT_OK;
+}
+
 int b200nufft_set_points(b200nufft_plan* p, int64_t M, const void* x, const void* y, const void* z, void* stream) {
   if (!p) return B200NUFFT_INVALID_ARGUMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanCall call(p, st);
   return p->is_double ? set_points_impl<double>(p, M, 0, x, y, z, st) : set_points_impl<float>(p, M, 0, x, y, z, st);
 }
 
 int b200nufft_set_points_interleaved(b200nufft_plan* p, int64_t M, const void* pts, void* stream) {
   if (!p) return B200NUFFT_INVALID_ARGUMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanCall call(p, st);
   return p->is_double ? set_points_impl<double>(p, M, 1, pts, nullptr, nullptr, st)
                       : set_points_impl<float>(p, M, 1, pts, nullptr, nullptr, st);
 }
@@ -1056,7 +1407,9 @@ int b200nufft_execute(b200nufft_plan* p, void* c, void* f, void* stream) {
   if (!p) return B200NUFFT_INVALID_ARGUMENT;
   if (p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "execute called on a spread-only plan");
   if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before execute");
+  if (!p->fine.p) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "execute: no workspace bound (external_workspace plan)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanCall call(p, st);
   return p->is_double ? execute_impl<double>(p, c, f, st) : execute_impl<float>(p, c, f, st);
 }
 
@@ -1065,6 +1418,7 @@ int b200nufft_interp(b200nufft_plan* p, void* c, const void* f, void* stream) {
   if (!p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "interp needs a spread-only plan");
   if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before interp");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanCall call(p, st);
   const size_t cs = p->is_double ? sizeof(double2) : sizeof(float2);
   for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
     const int ntr = std::min(p->batch, p->ntransf - b0);
@@ -1088,6 +1442,7 @@ int b200nufft_spread(b200nufft_plan* p, const void* c, void* f, void* stream) {
   if (!p->opts.spread_only) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "spread needs a spread-only plan");
   if (!p->points_set) return set_err(p, B200NUFFT_INVALID_ARGUMENT, "set_points must be called before spread");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanCall call(p, st);
   const size_t cs = p->is_double ? sizeof(double2) : sizeof(float2);
   for (int b0 = 0; b0 < p->ntransf; b0 += p->batch) {
     const int ntr = std::min(p->batch, p->ntransf - b0);
@@ -1132,10 +1487,12 @@ int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const v
   }
   if (cudaMemsetAsync(bin_sizes_out, 0, sizeof(int) * nbtot, st) != cudaSuccess) return B200NUFFT_INTERNAL;
   DevBuf k0, k1, v0, v1, hist, tmp;
+  MemCtx mem;
+  cudaGetDevice(&mem.device);
   int rc = B200NUFFT_OK;
   if (M > 0) {
-    if (k0.reserve(4 * M) || k1.reserve(4 * M) || v0.reserve(4 * M) || v1.reserve(4 * M) ||
-        hist.reserve(sizeof(int) * radix_hist_ints(M)) || tmp.reserve(sizeof(int) * (kScanMaxBlocks + 8))) {
+    if (k0.reserve(mem, 4 * M) || k1.reserve(mem, 4 * M) || v0.reserve(mem, 4 * M) || v1.reserve(mem, 4 * M) ||
+        hist.reserve(mem, sizeof(int) * radix_hist_ints(M)) || tmp.reserve(mem, sizeof(int) * (kScanMaxBlocks + 8))) {
       rc = B200NUFFT_RESOURCE_EXHAUSTED;
     } else {
       if (is_double)
@@ -1150,13 +1507,13 @@ int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const v
       cudaMemcpyAsync(idx_out, vs, sizeof(int) * M, cudaMemcpyDeviceToDevice, st);
     }
   } else {
-    tmp.reserve(sizeof(int) * (kScanMaxBlocks + 8));
+    tmp.reserve(mem, sizeof(int) * (kScanMaxBlocks + 8));
   }
   if (rc == B200NUFFT_OK) {
     exclusive_scan_i32(bin_sizes_out, bin_start_out, nbtot, tmp.as<int>(), nullptr, st);
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200NUFFT_INTERNAL;
   }
-  k0.release(); k1.release(); v0.release(); v1.release(); hist.release(); tmp.release();
+  k0.release(mem); k1.release(mem); v0.release(mem); v1.release(mem); hist.release(mem); tmp.release(mem);
   return rc;
 }
 

@@ -48,7 +48,9 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* total_out) {
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_chunk_sums_kernel(const int* __restrict__ in, int64_t n, int64_t chunk, int* __restrict__ block_sums) {
+scan_chunk_sums_kernel(const int* __restrict__ in, int64_t n, int64_t chunk, int* __restrict__ block_sums,
+                       const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   const int64_t beg = static_cast<int64_t>(blockIdx.x) * chunk;
   const int64_t end = min(beg + chunk, n);
   int s = 0;
@@ -59,7 +61,9 @@ scan_chunk_sums_kernel(const int* __restrict__ in, int64_t n, int64_t chunk, int
 }
 
 __global__ void __launch_bounds__(kScanMaxBlocks)
-scan_block_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total_out) {
+scan_block_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total_out,
+                       const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   __shared__ int wsum[32];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int v = t < nb ? block_sums[t] : 0;
@@ -79,7 +83,8 @@ scan_block_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ t
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int64_t n, int64_t chunk,
-                  const int* __restrict__ block_offs) {
+                  const int* __restrict__ block_offs, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   const int64_t beg = static_cast<int64_t>(blockIdx.x) * chunk;
   const int64_t end = min(beg + chunk, n);
   int carry = block_offs[blockIdx.x];
@@ -108,7 +113,9 @@ scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int64_t n, 
 // (subproblem counts, CalcSubproblemKernel nufft_plan.cu.cc:304-310, fused into the scan).
 constexpr int kScanSmallMax = 32768;
 __global__ void __launch_bounds__(1024)
-scan_small_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int div, int* __restrict__ total_out) {
+scan_small_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int div, int* __restrict__ total_out,
+                  const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   __shared__ int wsum[32];
   __shared__ int carry_s;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -138,23 +145,24 @@ scan_small_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int 
 }
 
 // tmp must hold kScanMaxBlocks ints. Returns the number of kernels launched.
+// skip (optional, device): when *skip != 0 every kernel returns at once (opts.reuse_points).
 inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_out,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, const int* skip = nullptr) {
   if (n <= 0) {
     if (total_out) cudaMemsetAsync(total_out, 0, sizeof(int), stream);
     return 0;
   }
   if (n <= kScanSmallMax) {
-    scan_small_kernel<<<1, 1024, 0, stream>>>(in, out, static_cast<int>(n), 0, total_out);
+    scan_small_kernel<<<1, 1024, 0, stream>>>(in, out, static_cast<int>(n), 0, total_out, skip);
     return 1;
   }
   int nb = static_cast<int>(std::min<int64_t>(kScanMaxBlocks, (n + 4 * kScanTile - 1) / (4 * kScanTile)));
   int64_t chunk = (n + nb - 1) / nb;
   chunk = ((chunk + kScanTile - 1) / kScanTile) * kScanTile;
   nb = static_cast<int>((n + chunk - 1) / chunk);
-  scan_chunk_sums_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, chunk, tmp);
-  scan_block_sums_kernel<<<1, kScanMaxBlocks, 0, stream>>>(tmp, nb, total_out);
-  scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, out, n, chunk, tmp);
+  scan_chunk_sums_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, chunk, tmp, skip);
+  scan_block_sums_kernel<<<1, kScanMaxBlocks, 0, stream>>>(tmp, nb, total_out, skip);
+  scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, out, n, chunk, tmp, skip);
   return 3;
 }
 
@@ -173,7 +181,8 @@ constexpr int kRadixBitsMax = 10;                          // 8-bit digits, or 1
 template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblk,
-                  int* __restrict__ hist /*[1 << BITS][nblk]*/) {
+                  int* __restrict__ hist /*[1 << BITS][nblk]*/, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   constexpr int RADIX = 1 << BITS;
   __shared__ int cnt[RADIX];
   for (int d = threadIdx.x; d < RADIX; d += kSortThreads) cnt[d] = 0;
@@ -192,7 +201,9 @@ template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int64_t n,
-                     int shift, int nblk, const int* __restrict__ offs /*[1 << BITS][nblk] scanned*/) {
+                     int shift, int nblk, const int* __restrict__ offs /*[1 << BITS][nblk] scanned*/,
+                     const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   constexpr int RADIX = 1 << BITS;
   __shared__ int cnt[kSortWarps][RADIX];   // running per-warp digit counts
   __shared__ int gbase[RADIX];             // global base of each digit for this block
@@ -251,7 +262,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
 // On return *keys_sorted/*vals_sorted point at whichever buffer holds the result.
 inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_t n, int key_bits,
                             int* hist, int* scan_tmp, uint32_t** keys_sorted, int** vals_sorted,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const int* skip = nullptr) {
   int launches = 0;
   uint32_t* kin = k0; int* vin = v0; uint32_t* kout = k1; int* vout = v1;
   if (n > 0) {
@@ -263,11 +274,11 @@ inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_
     const int passes = bits == 10 ? passes10 : passes8;
     for (int p = 0; p < passes; ++p) {
       const int shift = p * bits;
-      if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
-      else radix_hist_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist);
-      launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << bits) * nblk, scan_tmp, nullptr, stream);
-      if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
-      else radix_scatter_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist);
+      if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
+      else radix_hist_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
+      launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << bits) * nblk, scan_tmp, nullptr, stream, skip);
+      if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
+      else radix_scatter_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
       launches += 1;
       std::swap(kin, kout);
       std::swap(vin, vout);

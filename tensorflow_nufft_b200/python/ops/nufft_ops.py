@@ -6,7 +6,6 @@ reproduced here on the host, and all arithmetic is done by the CUDA engine throu
 (include/b200nufft.h). There is no CPU fallback: tensors that live on the host are copied to the
 current CUDA device and the result is copied back.
 """
-import collections
 import math
 import os
 
@@ -16,68 +15,41 @@ import torch
 from tensorflow_nufft_b200 import _lib
 from tensorflow_nufft_b200.python.ops import nufft_options
 
-_PLAN_CACHE = collections.OrderedDict()
-_PLAN_CACHE_SIZE = int(os.environ.get("B200NUFFT_PLAN_CACHE", "8"))
 _ENGINE_DEFAULTS = {}
-# Point-set reuse: a cached plan remembers which `points` tensor its bin-sort and
-# stencil records were built from (tensor identity + torch's in-place version counter) and skips
-# set_points when the same, unmodified tensor comes back -- the fixed-trajectory case of iterative
-# reconstruction (every CG iteration calls A and A^H with the same k-space trajectory). The plan
-# holds a reference to the tensor, so its memory cannot be recycled while the cache entry lives.
-_REUSE_POINTS = os.environ.get("B200NUFFT_REUSE_POINTS", "1") != "0"
-STATS = {"set_points_calls": 0, "set_points_skipped": 0}
+# Point-set reuse lives in the C library (opts.reuse_points): set_points fingerprints
+# the raw coordinates ON THE DEVICE and, when they equal the set the cached plan was built from,
+# every set_points kernel exits at once -- the fixed-trajectory case of iterative reconstruction
+# (every CG iteration calls A and A^H with the same k-space trajectory). It is content based, so
+# writes that bypass torch's version counter (DLPack aliases, raw-pointer libraries) cannot fool
+# it. Opt-in: B200NUFFT_REUSE_POINTS=1 or set_points_reuse(True).
+_REUSE_POINTS = os.environ.get("B200NUFFT_REUSE_POINTS", "0") != "0"
+STATS = {"set_points_calls": 0}
 
 
 def set_points_reuse(enabled):
-  """Enables / disables skipping set_points for an unchanged `points` tensor (default: enabled)."""
+  """Enables / disables the device-side unchanged-points shortcut of set_points (default: off)."""
   global _REUSE_POINTS
   _REUSE_POINTS = bool(enabled)
-  for p in _PLAN_CACHE.values():
-    p.points_token = None
-
-
-def _points_token(points):
-  # Device-resident tensors only: a host tensor may alias a numpy array that is modified behind
-  # torch's version counter. The token keeps the tensor (hence its storage) alive, so an equal
-  # address + layout + version can only be the same, unmodified memory (aliases such as
-  # `points.detach()` share the version counter).
-  if not (_REUSE_POINTS and points.is_cuda):
-    return None
-  return (points, points._version, tuple(points.shape), tuple(points.stride()), points.data_ptr(), points.dtype)
-
-
-def _same_points(token, points):
-  return (_REUSE_POINTS and token is not None and points.is_cuda and token[1] == points._version and
-          token[2] == tuple(points.shape) and token[3] == tuple(points.stride()) and
-          token[4] == points.data_ptr() and token[5] == points.dtype)
 
 
 def set_engine_defaults(**kwargs):
   """Engine knobs applied to every new plan (e.g. num_threads_compat=8, fseries_mode=0)."""
   _ENGINE_DEFAULTS.update(kwargs)
-  clear_plan_cache()
 
 
 def clear_plan_cache():
-  for p in _PLAN_CACHE.values():
-    p.close()
-  _PLAN_CACHE.clear()
+  """Destroys the idle plans of the library's process-level plan cache."""
+  _lib.plan_cache_clear()
 
 
 def _get_plan(key_args, opt_kwargs):
-  key = (key_args, tuple(sorted((k, tuple(v) if isinstance(v, (list, tuple)) else v)
-                                for k, v in opt_kwargs.items())))
-  plan = _PLAN_CACHE.get(key)
-  if plan is None:
-    ttype, grid_dims, sign, ntr, tol, dcode, device = key_args
-    plan = _lib.Plan(ttype, grid_dims, sign, ntr, tol, dcode, device=device, **opt_kwargs)
-    _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-      _, old = _PLAN_CACHE.popitem(last=False)
-      old.close()
-  else:
-    _PLAN_CACHE.move_to_end(key)
-  return plan
+  """Takes a plan from the C library's plan cache (b200nufft_plan_acquire); the caller gives it
+  back with plan.close() (b200nufft_plan_release). Keyed by every create argument."""
+  ttype, grid_dims, sign, ntr, tol, dcode, device = key_args
+  kw = dict(opt_kwargs)
+  if _REUSE_POINTS:
+    kw.setdefault("reuse_points", 1)
+  return _lib.Plan(ttype, grid_dims, sign, ntr, tol, dcode, device=device, cached=True, **kw)
 
 
 def _to_host(t):
@@ -116,6 +88,10 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
     raise ValueError("Input `points` must be a tensor")
   if source.dtype not in (torch.complex64, torch.complex128):
     raise ValueError(f"Input `source` must have type complex64 or complex128 but got: {source.dtype}")
+  # Lazy conjugate / negative views keep the parent's data_ptr: materialise them before any raw
+  # pointer reaches the engine (torch.conj(x), x.mH, ... would otherwise transform x itself).
+  source = source.resolve_conj().resolve_neg()
+  points = points.resolve_neg()
   rdtype = _real_dtype(source.dtype)
   if points.dtype != rdtype:
     raise ValueError(
@@ -232,41 +208,38 @@ def _run_op(source, points, grid_shape, transform_type, fft_direction, tol, opti
   with torch.cuda.device(dev_index):
     plan = _get_plan((ttype, grid_dims_xfast, sign, num_transforms, _op_tol(tol), dcode, dev_index),
                      opt_kwargs)
-    stream = torch.cuda.current_stream().cuda_stream
-    # mixed-radix decode of the call index over the outer dims (nufft_kernels.cc:512-523)
-    pf = [1] * len(outer)
-    sf = [1] * len(outer)
-    for d in range(len(outer) - 2, -1, -1):
-      pf[d] = pf[d + 1] * pts_outer_dims[d + 1]
-      sf[d] = sf[d + 1] * src_outer_dims[d + 1]
-    reuse = _REUSE_POINTS and num_calls == 1
-    for call in range(num_calls):
-      if reuse and _same_points(plan.points_token, points):
-        STATS["set_points_skipped"] += 1
-      else:
-        plan.points_token = None
+    try:
+      stream = torch.cuda.current_stream().cuda_stream
+      # mixed-radix decode of the call index over the outer dims (nufft_kernels.cc:512-523)
+      pf = [1] * len(outer)
+      sf = [1] * len(outer)
+      for d in range(len(outer) - 2, -1, -1):
+        pf[d] = pf[d + 1] * pts_outer_dims[d + 1]
+        sf[d] = sf[d + 1] * src_outer_dims[d + 1]
+      for call in range(num_calls):
         plan.set_points_interleaved(num_points, pts_p[call].data_ptr(), stream)
         STATS["set_points_calls"] += 1
-        plan.points_token = _points_token(points) if reuse else None
-      rem = call
-      sidx = 0
-      for d in range(len(outer)):
-        i_d = rem // pf[d]
-        rem = rem % pf[d]
-        if src_outer_dims[d] == 1:
-          i_d = 0
-        sidx += i_d * sf[d]
-      s_ptr = src_flat[sidx].data_ptr()
-      t_ptr = tgt_flat[call].data_ptr()
-      if op_type == "nufft":
-        if ttype == 1:
-          plan.execute(s_ptr, t_ptr, stream)
+        rem = call
+        sidx = 0
+        for d in range(len(outer)):
+          i_d = rem // pf[d]
+          rem = rem % pf[d]
+          if src_outer_dims[d] == 1:
+            i_d = 0
+          sidx += i_d * sf[d]
+        s_ptr = src_flat[sidx].data_ptr()
+        t_ptr = tgt_flat[call].data_ptr()
+        if op_type == "nufft":
+          if ttype == 1:
+            plan.execute(s_ptr, t_ptr, stream)
+          else:
+            plan.execute(t_ptr, s_ptr, stream)
+        elif op_type == "interp":
+          plan.interp(t_ptr, s_ptr, stream)
         else:
-          plan.execute(t_ptr, s_ptr, stream)
-      elif op_type == "interp":
-        plan.interp(t_ptr, s_ptr, stream)
-      else:
-        plan.spread(s_ptr, t_ptr, stream)
+          plan.spread(s_ptr, t_ptr, stream)
+    finally:
+      plan.close()   # back to the library's plan cache
 
   tgt_perm_shape = [out_batch[i] for i in order] + target_elem
   tgt = tgt_flat.reshape(tgt_perm_shape)
@@ -336,17 +309,10 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
     plans = {}
     for n in sorted(set(sizes), reverse=True):
       plans[n] = _get_plan((ttype, tuple(reversed(grid_shape)), sign, n, _op_tol(tol), dcode, dev_index), opt_kwargs)
-    pts = None
+    pts = points.to(device, non_blocking=True).reshape(num_points, -1)
     for n, pl in plans.items():
-      if _same_points(pl.points_token, points):
-        STATS["set_points_skipped"] += 1
-        continue
-      if pts is None:
-        pts = points.to(device, non_blocking=True).reshape(num_points, -1)
-      pl.points_token = None
       pl.set_points_interleaved(num_points, pts.data_ptr(), main.cuda_stream)
       STATS["set_points_calls"] += 1
-      pl.points_token = _points_token(points)
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
     out_ready = [torch.cuda.Event() for _ in range(2)]
@@ -376,6 +342,8 @@ def _run_host_pipelined(source, points, grid_shape, ttype, fft_direction, tol, o
       b0 += n
     main.wait_stream(copy_out)
     main.synchronize()
+    for pl in plans.values():
+      pl.close()   # back to the library's plan cache
   return out.reshape(target_shape)
 
 

@@ -183,34 +183,85 @@ def test_interp_3d_many_points_is_deterministic():
     assert torch.equal(out, first)
 
 
-def test_point_set_reuse_skips_set_points_and_tracks_in_place_updates():
-  """an unchanged device `points` tensor is sorted once per cached plan; an in-place
-  update (version counter) or a different tensor triggers a new set_points."""
-  tfft = _tfft()
-  from tensorflow_nufft_b200.python.ops import nufft_ops
-  tfft.clear_plan_cache()
-  tfft.set_points_reuse(True)
+def test_point_set_reuse_is_content_based_and_needs_no_host_sync():
+  """SURVEY 8f-4, in the C library: with opts.reuse_points the raw coordinates are fingerprinted on
+  the device; an unchanged set (even at another address) skips the sort, ANY change of content
+  -- including writes behind torch's version counter -- redoes it."""
+  from tensorflow_nufft_b200 import _lib
   src = torch.from_numpy(H.random_complex((4, 32, 40), 21)).cuda()
   pts = torch.from_numpy(H.uniform_points(5000, 2, 22)).cuda()
-  c0, s0 = nufft_ops.STATS["set_points_calls"], nufft_ops.STATS["set_points_skipped"]
-  a = tfft.nufft(src, pts)
-  b = tfft.nufft(src, pts)
-  b2 = tfft.nufft(src, pts.detach())      # alias: same memory, same version counter
-  assert nufft_ops.STATS["set_points_calls"] - c0 == 1
-  assert nufft_ops.STATS["set_points_skipped"] - s0 == 2
-  assert torch.equal(a, b) and torch.equal(a, b2)
-  pts.mul_(0.5)                           # in place: version bump -> re-sort
-  c = tfft.nufft(src, pts)
-  assert nufft_ops.STATS["set_points_calls"] - c0 == 2
-  want = tfft.nufft(src, pts.clone())     # different tensor -> re-sort, same values
-  assert nufft_ops.STATS["set_points_calls"] - c0 == 3
-  assert torch.equal(c, want) and not torch.equal(a, c)
-  tfft.set_points_reuse(False)
-  d = tfft.nufft(src, pts)
-  d2 = tfft.nufft(src, pts)
-  assert nufft_ops.STATS["set_points_calls"] - c0 == 5
-  assert torch.equal(d, d2) and torch.equal(d, c)
+  out = torch.empty((4, 5000), dtype=torch.complex64, device="cuda")
+  st = torch.cuda.current_stream().cuda_stream
+  plan = _lib.Plan(2, (40, 32), -1, 4, float(np.float32(1e-6)), _lib.COMPLEX64, device=0, reuse_points=1)
+
+  def run(p):
+    plan.set_points_interleaved(5000, p.data_ptr(), st)
+    plan.execute(out.data_ptr(), src.data_ptr(), st)
+    return out.clone()
+
+  a = run(pts)
+  b = run(pts)
+  assert plan.reuse_stats() == {"skipped": 1, "full": 1}
+  c = run(pts.clone())                      # other address, same content -> skipped
+  assert plan.reuse_stats() == {"skipped": 2, "full": 1}
+  assert torch.equal(a, b) and torch.equal(a, c)
+  alias = torch.as_strided(pts, (1,), (1,), 7)   # write through a view created behind the API
+  alias.fill_(0.123)
+  d = run(pts)
+  assert plan.reuse_stats() == {"skipped": 2, "full": 2}
+  ref_plan = _lib.Plan(2, (40, 32), -1, 4, float(np.float32(1e-6)), _lib.COMPLEX64, device=0)
+  ref_plan.set_points_interleaved(5000, pts.data_ptr(), st)
+  want = torch.empty_like(out)
+  ref_plan.execute(want.data_ptr(), src.data_ptr(), st)
+  assert torch.equal(d, want) and not torch.equal(d, a)
+  e = run(pts[:4000].contiguous())          # different M: never skipped
+  assert plan.reuse_stats()["full"] == 3
+  del e
+  plan.close()
+  ref_plan.close()
+
+
+def test_point_set_reuse_through_the_operator_and_plan_cache():
+  tfft = _tfft()
+  from tensorflow_nufft_b200 import _lib
+  tfft.clear_plan_cache()
+  src = torch.from_numpy(H.random_complex((4, 32, 40), 21)).cuda()
+  pts = torch.from_numpy(H.uniform_points(5000, 2, 22)).cuda()
+  base = tfft.nufft(src, pts)
+  h0 = _lib.plan_cache_stats()
   tfft.set_points_reuse(True)
+  try:
+    a = tfft.nufft(src, pts)
+    b = tfft.nufft(src, pts)
+    pts.mul_(0.5)
+    c = tfft.nufft(src, pts)
+  finally:
+    tfft.set_points_reuse(False)
+  want = tfft.nufft(src, pts)
+  h1 = _lib.plan_cache_stats()
+  assert torch.equal(a, base) and torch.equal(a, b) and torch.equal(c, want) and not torch.equal(a, c)
+  # 4 calls after the first: one new plan (the reuse_points variant), three served from the cache
+  assert h1["misses"] - h0["misses"] == 1 and h1["hits"] - h0["hits"] == 3
+
+
+def test_conjugate_views_are_resolved_before_the_engine_sees_them():
+  """torch.conj(x) is a lazy view with the parent's data_ptr."""
+  tfft = _tfft()
+  src = torch.from_numpy(H.random_complex((2, 24, 20), 3)).cuda()
+  pts = torch.from_numpy(H.uniform_points(700, 2, 4)).cuda()
+  lazy = torch.conj(src)
+  assert lazy.is_conj()
+  got = tfft.nufft(lazy, pts)
+  want = tfft.nufft(lazy.clone().resolve_conj(), pts)
+  assert torch.equal(got, want)
+  assert not torch.equal(got, tfft.nufft(src, pts))
+  c = torch.from_numpy(H.random_complex((2, 700), 5)).cuda()
+  got1 = tfft.nufft(c.conj(), pts, grid_shape=(24, 20), transform_type="type_1")
+  want1 = tfft.nufft(torch.conj(c).resolve_conj().clone(), pts, grid_shape=(24, 20), transform_type="type_1")
+  assert torch.equal(got1, want1)
+  assert torch.equal(tfft.interp(torch.conj(src), pts), tfft.interp(torch.conj(src).resolve_conj(), pts))
+  # host tensors take the same path
+  assert torch.equal(tfft.nufft(torch.conj(src.cpu()), pts.cpu()).cuda(), want)
 
 
 @pytest.mark.parametrize("stream_min", [0, 1 << 40])

@@ -206,11 +206,18 @@ def test_host_stream_chunking_policy():
   assert nufft_ops._host_chunk(small, 3, 10, (8, 8)) == 8
 
 
-def test_point_set_reuse_is_for_device_tensors_only():
-  """A host `points` tensor may alias a numpy array that changes behind torch's version counter:
-  it never yields a reuse token."""
-  import torch
+def test_point_set_reuse_is_opt_in_and_lives_in_the_c_library(L):
+  """The unchanged-points shortcut is a b200nufft_opts field (device-side fingerprint), off by
+  default; the Python mirror only forwards the switch."""
+  from tensorflow_nufft_b200 import _lib
   from tensorflow_nufft_b200.python.ops import nufft_ops
-  pts = torch.zeros((10, 2))
-  assert nufft_ops._points_token(pts) is None
-  assert not nufft_ops._same_points(None, pts)
+  assert _lib.make_opts().reuse_points == 0
+  assert _lib.make_opts(reuse_points=1).reuse_points == 1
+  assert os.environ.get("B200NUFFT_REUSE_POINTS", "0") != "0" or not nufft_ops._REUSE_POINTS
+  # the plan cache is the library's, not Python's
+  stats = _lib.plan_cache_stats()
+  assert set(stats) == {"hits", "misses", "idle"}
+  _lib.plan_cache_clear()
+  assert _lib.plan_cache_stats()["idle"] == 0
+  a, f = _lib.alloc_counts()
+  assert a >= f >= 0
