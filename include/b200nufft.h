@@ -78,8 +78,9 @@ typedef struct b200nufft_opts {
   int bin_dims[3];         /* engine bin geometry (cf. InternalOptions::gpu_bin_size); 0 = auto   */
   int max_subproblem_size; /* points per subproblem (cf. gpu_max_subproblem_size = 1024); 0 = auto */
   int spread_method;       /* 0 auto, 1 global-atomic point-driven, 2 shared-memory tiles,
-                              3 window-sorted register runs, 4 same with even-row windows (2D
-                              type-1 NUFFT plans; falls back to 3 elsewhere)                      */
+                              3 window-sorted register runs, 4 same with even-row windows, 6 window
+                              swept along x with rotating row accumulators (4 and 6: 2D type-1
+                              NUFFT plans; they fall back to 3 elsewhere)                         */
   int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged),
                               lanes over one point's stencil, 3 shared-memory tiles, quarter warp
                               per point                                                           */
@@ -95,7 +96,8 @@ typedef struct b200nufft_opts {
                               caller binds a block with b200nufft_bind_workspace                  */
   int reserved[8];         /* engine A/B switches used by the tests and probes (0 = default):
                               [0] 1: stage interpolator tiles with cp.async instead of TMA
-                              [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8)
+                              [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8, 16)
+                              [3] 1: sweep spreaders use scalar FFMA instead of packed FFMA2
                               [4] 1: single cuFFT 3D plan instead of the pruned three-plan scheme
                               [5] 1: flush spreader tiles with REDG instead of TMA reduce-add
                               [6] 1: 3D tiles move all their z-planes (no per-subproblem z range) */
@@ -114,6 +116,8 @@ typedef struct b200nufft_info {
   int num_threads_compat;
   int64_t num_points;
   int64_t subproblem_bound; /* upper bound on subproblem count used for the launch grid     */
+  int spread_method;       /* kernel family actually selected (values of opts.spread_method; 5 = row-lane tiles) */
+  int interp_method;       /* ... (values of opts.interp_method; 5 = row-lane tiles)       */
 } b200nufft_info;
 
 void b200nufft_default_opts(b200nufft_opts* opts);

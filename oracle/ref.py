@@ -10,6 +10,8 @@ Modes:
   mode="gpuparams"  the same CPU code driven with Plan<GPUDevice>'s choices
                     (sigma = 2.0, direct exp(sqrt) evaluation; nufft_plan.cu.cc:1849-1857):
                     the parity target for the CUDA engine.
+  mode="lowups_direct"  sigma = 1.25 (the CPU plan's choice for large grids, nufft_plan.h:745-752)
+                    with direct evaluation: the parity target of the engine's opts.upsampling = 1.
 `tol` is cast through float32 exactly like the op attr (nufft_ops.cc:214, nufft_kernels.cc:361)
 unless tol_is_exact=True.
 """
@@ -97,6 +99,8 @@ class RefPlan:
       upsampfac, kerevalmeth = 2.0, 1
     elif mode == "horner2":   # sigma=2 but Horner: isolates the evaluator difference
       upsampfac, kerevalmeth = 2.0, 2
+    elif mode == "lowups_direct":   # sigma=1.25 with direct evaluation: parity target of opts.upsampling=1
+      upsampfac, kerevalmeth = 1.25, 1
     else:
       raise ValueError(mode)
     err = ctypes.create_string_buffer(512)

@@ -71,9 +71,34 @@ class Tensor {
   std::shared_ptr<void> buf_;
   int64_t n_ = 0;
 };
+// ---- GPU-side pieces named by tensorflow_nufft_b200/tf_glue/nufft_kernels_b200.cc (syntax check of
+// the glue only; signatures follow TF 2.11: framework/allocator.h, framework/device_base.h) ----
+struct AllocatorAttributes {};
+class Allocator {
+ public:
+  static constexpr size_t kAllocatorAlignment = 64;
+  virtual ~Allocator() {}
+  virtual void* AllocateRaw(size_t alignment, size_t num_bytes) { return std::aligned_alloc(alignment, (num_bytes + alignment - 1) / alignment * alignment); }
+  virtual void DeallocateRaw(void* ptr) { std::free(ptr); }
+};
+class DeviceBase {
+ public:
+  struct CpuWorkerThreads { int num_threads = 1; };
+  struct AcceleratorDeviceInfo { int gpu_id = 0; };
+  const CpuWorkerThreads* tensorflow_cpu_worker_threads() const { return &cpu_; }
+  const AcceleratorDeviceInfo* tensorflow_accelerator_device_info() const { return &acc_; }
+  Allocator* GetAllocator(AllocatorAttributes) { return &alloc_; }
+ private:
+  CpuWorkerThreads cpu_;
+  AcceleratorDeviceInfo acc_;
+  Allocator alloc_;
+};
 class OpKernelContext {
  public:
   Status allocate_temp(DataType d, const TensorShape& s, Tensor* t) { t->Alloc(d, s.num_elements()); return OkStatus(); }
   template <typename D> const D& eigen_device() const { static D d; return d; }
+  DeviceBase* device() const { return const_cast<DeviceBase*>(&dev_); }
+ private:
+  DeviceBase dev_;
 };
 }  // namespace tensorflow

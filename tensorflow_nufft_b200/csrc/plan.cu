@@ -32,6 +32,7 @@
 #include "spread.cuh"
 #include "spread_ws.cuh"
 #include "spread_ws2.cuh"
+#include "spread_sweep.cuh"
 
 using namespace b200;
 
@@ -318,7 +319,7 @@ constexpr int kInterpWarps = 4;
 // 2.59 ms (2), 2.79 ms (4).
 constexpr int kSpreadWarps3D = 1;
 
-bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z);
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z, int halo_x = 8);
 
 template <int RANK, int WPT>
 cudaError_t launch_spread_tile(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
@@ -393,6 +394,34 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
   return cudaGetLastError();
 }
 
+template <int Y>
+cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  constexpr int NC = 4 * Y;
+  const int ngroups = ntr / NC;
+  const int64_t nblocks = p->sub_bound * ngroups;
+  if (nblocks > 2147483647LL) return cudaErrorInvalidValue;
+  const size_t smem = spread_sweep2d_smem_bytes<Y>(p->bin);
+  const int use_tma = (p->opts.reserved[5] == 0 &&
+                       ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, 0, kSweepHaloX)) ? 1 : 0;
+  const bool pack = p->opts.reserved[3] == 0;
+#define SWEEP_CASE(NS)                                                                            \
+  case NS: {                                                                                     \
+    auto k = pack ? spread_sweep2d_f32_kernel<NS, Y, 1> : spread_sweep2d_f32_kernel<NS, Y, 0>;   \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<static_cast<unsigned>(nblocks), 32, smem, st>>>(p->M, g, ngroups, p->sub_total(), p->sub_desc.as<int4>(), \
+                              p->idx, p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef SWEEP_CASE
+  return cudaGetLastError();
+}
+
 // Builds (or reuses) the TMA tensor map of a fine-grid batch [ntr][nf2][nf1][2*nf0] float32 with a
 // box of one tile. cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -450,8 +479,8 @@ bool ensure_tile_map(const b200nufft_plan* p, b200nufft_plan::TileMap* tm, const
 }
 
 // The spreaders' output map: box = one (bin + 8)^rank tile of one transform.
-bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z = 0) {
-  return ensure_tile_map(p, &p->tmap_out, grid, ntr, p->bin[0] + 8, p->bin[1] + 8, 1, box_z);
+bool ensure_out_tensor_map(b200nufft_plan* p, const void* grid, int ntr, int box_z, int halo_x) {
+  return ensure_tile_map(p, &p->tmap_out, grid, ntr, p->bin[0] + halo_x, p->bin[1] + 8, 1, box_z);
 }
 
 template <int RANK>
@@ -554,6 +583,25 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
   if (p->spread_method == 5) {
     cudaError_t e = launch_spread_rowlane<F>(p, ntr, static_cast<const Cplx<F>*>(c), static_cast<Cplx<F>*>(fw), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread rowlane launch: %s", cudaGetErrorString(e));
+  } else if (p->spread_method == 6) {
+    cudaError_t e;
+    const float2* cc = static_cast<const float2*>(c);
+    float2* ff = static_cast<float2*>(fw);
+    const int nc_opt = p->opts.reserved[1];   // coils per CTA override (0 = auto)
+    const int nc = nc_opt > 0 ? nc_opt : 8;
+    if (nc >= 16 && ntr % 16 == 0) e = launch_spread_sweep2d<4>(p, ntr, cc, ff, st);
+    else if (nc >= 8 && ntr % 8 == 0) e = launch_spread_sweep2d<2>(p, ntr, cc, ff, st);
+    else if (ntr % 4 == 0) e = launch_spread_sweep2d<1>(p, ntr, cc, ff, st);
+    else {
+      // coil counts that are not a multiple of 4: groups of 4 through the sweep kernel, the rest
+      // through the window-sorted kernel (same records, same sort)
+      const int main_n = ntr & ~3;
+      e = cudaSuccess;
+      if (main_n > 0) e = launch_spread_sweep2d<1>(p, main_n, cc, ff, st);
+      for (int k = main_n; k < ntr && e == cudaSuccess; ++k)
+        e = launch_spread_ws2<1>(p, 1, cc + static_cast<int64_t>(k) * p->M, ff + static_cast<int64_t>(k) * p->nftot, st);
+    }
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread sweep launch: %s", cudaGetErrorString(e));
   } else if (p->spread_method == 4) {
     cudaError_t e;
     const float2* cc = static_cast<const float2*>(c);
@@ -932,7 +980,23 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
 template <typename F>
 int create_impl(b200nufft_plan* p) {
   // ---- kernel + grid parameters (setup_spreader, set_grid_size) ----
-  const double sigma = 2.0;  // Plan<GPUDevice> always uses 2.0 (nufft_plan.cu.cc:1855-1857)
+  // Upsampling factor. Plan<GPUDevice> always uses 2.0 (nufft_plan.cu.cc:1855-1857): the default.
+  // opts.upsampling = 1: sigma = 1.25 (smaller FFT, wider kernel); 2: the CPU plan's automatic choice
+  // (PlanBase::set_default_options, nufft_plan.h:739-752): 1.25 for large grids at tol >= 1e-9.
+  // Interp / Spread ops are pinned to 2.0 (nufft_kernels.cc:457-460).
+  double sigma = 2.0;
+  if (!p->opts.spread_only) {
+    if (p->opts.upsampling == 1) sigma = 1.25;
+    else if (p->opts.upsampling == 2) {
+      if (static_cast<F>(p->tol) >= F(1e-9)) {
+        const int64_t gs = p->n_modes_tot;
+        if ((p->rank == 1 && gs > 10000000) || (p->rank == 2 && gs > 300000) || (p->rank == 3 && gs > 3000000)) sigma = 1.25;
+      }
+    } else if (p->opts.upsampling != 0) {
+      return set_err(p, B200NUFFT_INVALID_ARGUMENT, "opts.upsampling must be 0 (2.0), 1 (1.25) or 2 (automatic), got %d",
+                     p->opts.upsampling);
+    }
+  }
   p->kp = make_kernel_params<F>(static_cast<F>(p->tol), sigma);
   p->nftot = 1;
   for (int d = 0; d < p->rank; ++d) {
@@ -971,7 +1035,7 @@ int create_impl(b200nufft_plan* p) {
   // 3 for spread-only plans); 3D -> plane-owner tile kernel (2)
   // (measured on B200, cfg2 per 32 coils: 1.38 ms (4) vs 1.70 ms (3) vs 4.5 ms (2); cfg3: 3.2 ms
   //  tile vs >= 4.0 ms window-sorted)
-  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 4 : 2) : 1) : p->opts.spread_method;
+  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 6 : 2) : 1) : p->opts.spread_method;
   // interpolator: 3 = quarter-warp gather (measured: cfg2-type2 0.56 vs 0.92 ms per 8 coils, cfg3-type2
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
@@ -986,8 +1050,10 @@ int create_impl(b200nufft_plan* p) {
     p->rl_lp = p->PY <= 8 ? 8 : 16;
   }
   // ws2 is 2D, type-1 NUFFT plans only (its records are not usable by the other kernels)
-  if (p->spread_method == 4 && (p->rank != 2 || p->type != 1 || p->opts.spread_only)) p->spread_method = 3;
-  const bool ws_any = p->spread_method == 3 || p->spread_method == 4;
+  // ws2 (4) and the sweep spreader (6) are 2D, type-1 NUFFT plans only (their records carry a row shift)
+  if ((p->spread_method == 4 || p->spread_method == 6) && (p->rank != 2 || p->type != 1 || p->opts.spread_only))
+    p->spread_method = 3;
+  const bool ws_any = p->spread_method == 3 || p->spread_method == 4 || p->spread_method == 6;
   int def_bin[3] = {1, 1, 1};
   if (p->rank == 1) { def_bin[0] = 1024; }
   else if (p->rank == 2) {
@@ -1021,7 +1087,7 @@ int create_impl(b200nufft_plan* p) {
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && ws_any;
-  p->ws2 = p->ws && p->spread_method == 4;
+  p->ws2 = p->ws && (p->spread_method == 4 || p->spread_method == 6);
   if (p->ws2 && (p->bin[1] & 1))
     return set_err(p, B200NUFFT_INVALID_ARGUMENT, "even-row window spreader needs an even bin_dims[1]");
   if (p->ws && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)
@@ -1043,7 +1109,8 @@ int create_impl(b200nufft_plan* p) {
     if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
-    if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
+    if (uses_tile && p->spread_method == 6) need = std::max(need, spread_sweep2d_smem_bytes<4>(p->bin));
+    else if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
     if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin, 8) : interp_qw_smem_bytes<3>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
@@ -1546,6 +1613,8 @@ int b200nufft_get_info(const b200nufft_plan* p, b200nufft_info* info) {
   info->num_threads_compat = p->num_threads_compat;
   info->num_points = p->M;
   info->subproblem_bound = p->sub_bound;
+  info->spread_method = (p->type == 1 || p->opts.spread_only) ? p->spread_method : 0;
+  info->interp_method = (p->type == 2 || p->opts.spread_only) ? p->interp_method : 0;
   return B200NUFFT_OK;
 }
 

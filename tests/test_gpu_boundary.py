@@ -76,7 +76,10 @@ def test_caller_owned_workspace_matches_plan_owned_buffers(ttype, rank):
   plan.bind_workspace(ws.data_ptr(), nbytes, m)
   got = _run(plan, pts, src, out, ttype)
   assert L.alloc_counts() == a_created, "a workspace-bound plan must not allocate"
-  assert torch.equal(got, want)
+  if ttype == 2:
+    assert torch.equal(got, want)
+  else:   # type 1 sums through global reductions: same values, bits depend on arrival order
+    assert H.rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 1e-6
   with pytest.raises(L.NufftError, match="workspace was bound for"):
     big = torch.from_numpy(H.uniform_points(2 * m, rank, 33)).cuda()
     plan.set_points_interleaved(2 * m, big.data_ptr(), torch.cuda.current_stream().cuda_stream)

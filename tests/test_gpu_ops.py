@@ -195,7 +195,7 @@ def test_point_set_reuse_is_content_based_and_needs_no_host_sync():
   plan = _lib.Plan(2, (40, 32), -1, 4, float(np.float32(1e-6)), _lib.COMPLEX64, device=0, reuse_points=1)
 
   def run(p):
-    plan.set_points_interleaved(5000, p.data_ptr(), st)
+    plan.set_points_interleaved(p.shape[0], p.data_ptr(), st)
     plan.execute(out.data_ptr(), src.data_ptr(), st)
     return out.clone()
 
@@ -214,9 +214,10 @@ def test_point_set_reuse_is_content_based_and_needs_no_host_sync():
   want = torch.empty_like(out)
   ref_plan.execute(want.data_ptr(), src.data_ptr(), st)
   assert torch.equal(d, want) and not torch.equal(d, a)
-  e = run(pts[:4000].contiguous())          # different M: never skipped
-  assert plan.reuse_stats()["full"] == 3
-  del e
+  e = run(pts[:4000])                       # different M (a prefix of the same memory): never skipped
+  assert plan.reuse_stats() == {"skipped": 2, "full": 3}
+  e2 = run(pts[:4000])
+  assert plan.reuse_stats() == {"skipped": 3, "full": 3} and torch.equal(e[:, :4000], e2[:, :4000])
   plan.close()
   ref_plan.close()
 
@@ -258,7 +259,9 @@ def test_conjugate_views_are_resolved_before_the_engine_sees_them():
   c = torch.from_numpy(H.random_complex((2, 700), 5)).cuda()
   got1 = tfft.nufft(c.conj(), pts, grid_shape=(24, 20), transform_type="type_1")
   want1 = tfft.nufft(torch.conj(c).resolve_conj().clone(), pts, grid_shape=(24, 20), transform_type="type_1")
-  assert torch.equal(got1, want1)
+  # type 1 sums through global reductions: same values, bits depend on arrival order
+  assert H.rel_l2(got1.cpu().numpy(), want1.cpu().numpy()) < 1e-6
+  assert H.rel_l2(got1.cpu().numpy(), tfft.nufft(c, pts, grid_shape=(24, 20), transform_type="type_1").cpu().numpy()) > 0.1
   assert torch.equal(tfft.interp(torch.conj(src), pts), tfft.interp(torch.conj(src).resolve_conj(), pts))
   # host tensors take the same path
   assert torch.equal(tfft.nufft(torch.conj(src.cpu()), pts.cpu()).cuda(), want)

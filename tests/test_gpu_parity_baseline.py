@@ -1,0 +1,288 @@
+"""GPU parity tests on the BASELINE.json configurations at their real sizes:
+engine vs the reference's own compiled CPU plan (oracle/_ref/libref.so) driven with the GPU plan's
+parameter choices (sigma = 2, direct kernel evaluation; SURVEY 8c `ref_cpu_gpuparams`).
+
+Gates (BASELINE.json north_star): relative L2 <= max(2 tol, 1e-6) for complex64, <= 2 tol for
+complex128."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+NTHR = os.cpu_count() or 1
+
+
+def _tfft():
+  import tensorflow_nufft_b200 as tfft
+  tfft.set_engine_defaults(num_threads_compat=NTHR)
+  return tfft
+
+
+def _ref():
+  from oracle import ref
+  if not ref.available():
+    pytest.skip("oracle/_ref/libref.so not built")
+  return ref
+
+
+def _plan_pts(pts):
+  return np.ascontiguousarray(pts[:, ::-1].T)
+
+
+@pytest.mark.parametrize("coils", [8, 32])
+def test_cfg2_full_size_many_coils(coils):
+  """cfg2 with the coil counts the benchmark runs (8 coils per CTA is the kernel BENCH times:
+  spread_ws2<7,8> / its successors), all 2M spiral points."""
+  tfft, ref = _tfft(), _ref()
+  from tensorflow_nufft_b200 import _lib
+  grid = (512, 512)
+  pts = H.spiral_points(32, 62500)
+  M = pts.shape[0]
+  src = H.random_complex((coils, M), 61)
+  out = tfft.nufft(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid_shape=grid,
+                   transform_type="type_1", fft_direction="backward", tol=1e-6).cpu().numpy()
+  rp = ref.RefPlan(1, [512, 512], 1, coils, 1e-6, np.complex64, mode="gpuparams", num_threads=NTHR)
+  rp.set_points(_plan_pts(pts))
+  want = rp.execute(src)
+  rp.close()
+  err = H.rel_l2(out.reshape(coils, -1), want)
+  assert err <= 2e-6, f"cfg2 x{coils}: rel L2 {err:.3e}"
+  worst = max(H.rel_l2(out[t].reshape(-1), want[t]) for t in range(coils))   # no coil hides behind the others
+  assert worst <= 2e-6, f"cfg2 x{coils}: worst coil {worst:.3e}"
+  # the type-2 mirror on the same points and coil count (interpolator with 8 coils per CTA)
+  img = H.random_complex((coils,) + grid, 62)
+  out2 = tfft.nufft(torch.from_numpy(img).cuda(), torch.from_numpy(pts).cuda(), transform_type="type_2",
+                    fft_direction="forward", tol=1e-6).cpu().numpy()
+  rp = ref.RefPlan(2, [512, 512], -1, coils, 1e-6, np.complex64, mode="gpuparams", num_threads=NTHR)
+  rp.set_points(_plan_pts(pts))
+  want2 = rp.execute(img.reshape(coils, -1))
+  rp.close()
+  err2 = H.rel_l2(out2, want2)
+  assert err2 <= 2e-6, f"cfg2 type-2 mirror x{coils}: rel L2 {err2:.3e}"
+  plan = _lib.Plan(1, (512, 512), 1, coils, float(np.float32(1e-6)), _lib.COMPLEX64, device=0)
+  assert plan.info().spread_method >= 2, "cfg2 must run a shared-memory tile spreader"
+  plan.close()
+
+
+def test_cfg4_full_size_single_coil():
+  """cfg4 at its real size: 256^3 grid (fine grid 512^3: 64-bit offsets, 262144-bin scans, the
+  pruned three-plan FFT, deep bins with z-trimmed TMA boxes), 4M stack-of-stars points, one coil with
+  max_batch_size = 1 as SURVEY 8c prescribes."""
+  tfft, ref = _tfft(), _ref()
+  grid = (256, 256, 256)
+  pts = H.stack_of_stars_points(125, 125, 256)
+  M = pts.shape[0]
+  src = H.random_complex(grid, 71)
+  opts = tfft.Options()
+  opts.max_batch_size = 1
+  out = tfft.nufft(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), transform_type="type_2",
+                   fft_direction="forward", tol=1e-6, options=opts).cpu().numpy()
+  rp = ref.RefPlan(2, [256, 256, 256], -1, 1, 1e-6, np.complex64, mode="gpuparams", num_threads=NTHR,
+                   max_batch_size=1)
+  rp.set_points(_plan_pts(pts))
+  want = rp.execute(src.reshape(1, -1))[0]
+  rp.close()
+  assert rp.fine_dims == [512, 512, 512]
+  err = H.rel_l2(out, want)
+  assert err <= 2e-6, f"cfg4 full size: rel L2 {err:.3e}"
+  # and the adjoint (type 1) on the same sparse point set: the 3D spreader at nf = 512^3
+  c = H.random_complex((M,), 72)
+  out1 = tfft.nufft(torch.from_numpy(c).cuda(), torch.from_numpy(pts).cuda(), grid_shape=grid,
+                    transform_type="type_1", fft_direction="backward", tol=1e-6, options=opts).cpu().numpy()
+  rp = ref.RefPlan(1, [256, 256, 256], 1, 1, 1e-6, np.complex64, mode="gpuparams", num_threads=NTHR,
+                   max_batch_size=1)
+  rp.set_points(_plan_pts(pts))
+  want1 = rp.execute(c.reshape(1, -1))[0]
+  rp.close()
+  err1 = H.rel_l2(out1.reshape(-1), want1)
+  assert err1 <= 2e-6, f"cfg4 adjoint full size: rel L2 {err1:.3e}"
+
+
+def test_cfg5_forward_and_both_gradients_at_size():
+  """cfg5: 2D type-2, 256^2, complex128, tol 1e-12, M = 100k radial points; the forward result and
+  the gradients w.r.t. source and points (torch autograd through the operator mirror) against the
+  oracle COMPOSED THE SAME WAY as `_nufft_grad`
+  (/root/reference/tensorflow_nufft/python/ops/nufft_ops.py:126-232): grad_source = one
+  opposite-type, opposite-direction transform of the upstream gradient; grad_points = Re of
+  (one T = rank type-2 transform of source * grid coordinates) * conj(upstream) * (-i). Gate 2 tol."""
+  tfft, ref = _tfft(), _ref()
+  tol = 1e-12
+  grid = (256, 256)
+  pts = H.radial_points(200, 500, np.float64)
+  M = pts.shape[0]
+  src = H.random_complex(grid, 81, np.complex128)
+  up = H.random_complex((M,), 82, np.complex128)
+  t_src = torch.from_numpy(src).cuda().requires_grad_(True)
+  t_pts = torch.from_numpy(pts).cuda().requires_grad_(True)
+  out = tfft.nufft(t_src, t_pts, transform_type="type_2", fft_direction="forward", tol=tol)
+  loss = torch.real((out * torch.from_numpy(up).cuda()).sum())
+  g_src, g_pts = torch.autograd.grad(loss, [t_src, t_pts])
+  pp = _plan_pts(pts)
+
+  def ref_exec(ttype, sign, T, data):
+    rp = ref.RefPlan(ttype, [256, 256], sign, T, tol, np.complex128, mode="gpuparams", num_threads=NTHR)
+    assert rp.kernel_width == 14    # the float attr turns 1e-12 into 9.99999996e-13
+    rp.set_points(pp)
+    res = rp.execute(data)
+    rp.close()
+    return res
+
+  want = ref_exec(2, -1, 1, src.reshape(1, -1))[0]
+  err = H.rel_l2(out.detach().cpu().numpy(), want)
+  assert err <= 2 * tol, f"cfg5 forward: rel L2 {err:.3e}"
+
+  # d loss / d source: loss = Re sum(out * up); torch's convention returns conj(dL/dsource^*)...
+  # `_nufft_grad` (reference :150-163): grad_source = nufft(grad, type_1, backward) with
+  # grad = conj-convention upstream = conj(up) in torch's real-loss convention
+  grad_up = np.conj(up)
+  want_gs = ref_exec(1, 1, 1, grad_up.reshape(1, -1))[0].reshape(grid)
+  err_gs = H.rel_l2(g_src.cpu().numpy(), want_gs)
+  assert err_gs <= 2 * tol, f"cfg5 grad_source: rel L2 {err_gs:.3e}"
+
+  # d loss / d points (reference :165-216)
+  gv = [np.arange(n, dtype=np.float64) - n / 2 for n in grid]
+  gp = np.stack(np.meshgrid(*gv, indexing="ij"), 0)                      # [rank, 256, 256]
+  t2 = ref_exec(2, -1, 2, (src[None] * gp).reshape(2, -1))               # [rank, M]
+  want_gp = np.real(t2 * np.conj(grad_up)[None, :] * (-1j)).T            # [M, rank]
+  err_gp = H.rel_l2(g_pts.cpu().numpy(), want_gp)
+  assert err_gp <= 2 * tol, f"cfg5 grad_points: rel L2 {err_gp:.3e}"
+
+
+CASES_IS = [
+    # grid (TF order), M, T, dtype, tol
+    ((64, 96), 30000, 1, np.complex64, 1e-6),
+    ((64, 96), 30000, 3, np.complex64, 1e-4),
+    ((48, 40), 9000, 2, np.complex128, 1e-12),
+    ((32, 48, 40), 50000, 1, np.complex64, 1e-6),
+    ((32, 48, 40), 20000, 2, np.complex64, 1e-3),
+    ((24, 32, 36), 12000, 2, np.complex128, 1e-9),
+    ((120,), 3000, 2, np.complex64, 1e-6),
+]
+
+
+@pytest.mark.parametrize("grid,M,T,cd,tol", CASES_IS)
+def test_interp_and_spread_ops_match_reference_plan(grid, M, T, cd, tol):
+  """`tfft.interp` / `tfft.spread` against the reference plan's own interp / spread
+  (nufft_plan.cc; GPU: nufft_plan.cu.cc:2170-2225) incl. kernel_scale (nufft_util.cc:43-62). The ops
+  have no options attr: points_range = STRICT."""
+  tfft, ref = _tfft(), _ref()
+  rank = len(grid)
+  rd = np.float32 if cd == np.complex64 else np.float64
+  pts = H.uniform_points(M, rank, 91, rd) * rd(0.999)
+  pp = _plan_pts(pts)
+  f = H.random_complex((T,) + grid, 92, cd)
+  c = H.random_complex((T, M), 93, cd)
+  gate = max(2 * tol, 1e-6) if cd == np.complex64 else 2 * float(np.float32(tol))
+
+  got_i = tfft.interp(torch.from_numpy(f).cuda(), torch.from_numpy(pts).cuda(), tol=tol).cpu().numpy()
+  rp = ref.RefPlan(2, list(grid[::-1]), -1, T, tol, cd, mode="gpuparams", points_range="strict",
+                   num_threads=NTHR, spread_only=True)
+  rp.set_points(pp)
+  want_i = rp.interp(f.reshape(T, -1))
+  scale = rp.kernel_scale
+  rp.close()
+  assert scale > 0
+  err = H.rel_l2(got_i, want_i)
+  assert err <= gate, f"interp {grid} {cd.__name__}: rel L2 {err:.3e}"
+
+  got_s = tfft.spread(torch.from_numpy(c).cuda(), torch.from_numpy(pts).cuda(), grid, tol=tol).cpu().numpy()
+  rp = ref.RefPlan(1, list(grid[::-1]), -1, T, tol, cd, mode="gpuparams", points_range="strict",
+                   num_threads=NTHR, spread_only=True)
+  rp.set_points(pp)
+  want_s = rp.spread(c)
+  rp.close()
+  err = H.rel_l2(got_s.reshape(T, -1), want_s)
+  assert err <= gate, f"spread {grid} {cd.__name__}: rel L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("grid", [(62, 64), (64, 66), (12, 64), (64, 63), (22, 64, 64)])
+def test_interp_spread_reject_grids_that_are_not_fine_grids(grid):
+  """Spread-only plans take the grid as the fine grid: it must be even, 2-3-5 smooth and at least
+  twice the kernel width (InvalidArgument nufft_plan.h:830-837; the GPU plan returns Internal with
+  the same text, nufft_plan.cu.cc:3195-3201). Same verdict as the reference plan."""
+  tfft, ref = _tfft(), _ref()
+  rank = len(grid)
+  pts = torch.from_numpy(H.uniform_points(100, rank, 3) * np.float32(0.99)).cuda()
+  f = torch.zeros(grid, dtype=torch.complex64).cuda()
+  c = torch.zeros(100, dtype=torch.complex64).cuda()
+  with pytest.raises(ValueError, match="Invalid grid"):
+    ref.RefPlan(2, list(grid[::-1]), -1, 1, 1e-6, np.complex64, mode="gpuparams", spread_only=True)
+  with pytest.raises(ValueError, match="Invalid grid size: .* even, larger than the kernel .14. and have no prime factors larger than 5"):
+    tfft.interp(f, pts)
+  with pytest.raises(ValueError, match="Invalid grid size"):
+    tfft.spread(c, pts, grid)
+
+
+def test_selected_kernels_are_tile_kernels_for_north_star_configs():
+  """No north_star configuration (2D / 3D, complex64 / complex128, tol 1e-6 ... 1e-12) may fall to
+  the point-driven global-memory kernels (method 1)."""
+  from tensorflow_nufft_b200 import _lib
+  for rank, dcode, tol in [(2, _lib.COMPLEX64, 1e-6), (3, _lib.COMPLEX64, 1e-6), (2, _lib.COMPLEX128, 1e-12),
+                           (3, _lib.COMPLEX128, 1e-12), (3, _lib.COMPLEX128, 1e-6), (3, _lib.COMPLEX64, 1e-7),
+                           (2, _lib.COMPLEX64, 1e-7)]:
+    dims = (64,) * rank
+    for ttype in (1, 2):
+      plan = _lib.Plan(ttype, dims, -1, 1, float(np.float32(tol)), dcode, device=0)
+      info = plan.info()
+      m = info.spread_method if ttype == 1 else info.interp_method
+      plan.close()
+      assert m >= 2, f"rank {rank} dtype {dcode} tol {tol} type {ttype}: point-driven kernel selected"
+
+
+@pytest.mark.parametrize("case", ["2d", "3d", "3d_sparse", "2d_f64"])
+def test_low_upsampling_mode_matches_reference_direct(case):
+  """sigma = 1.25 (opts.upsampling = 1; width and beta per nufft_plan.h:769-771 /
+  nufft_plan.cu.cc:3089-3092) against the reference CPU plan with the same sigma and direct kernel
+  evaluation (Horner tables stay out of scope), both transform types."""
+  ref = _ref()
+  _tfft()
+  from tensorflow_nufft_b200.python.ops import nufft_ops
+  cd = np.complex64
+  tol = 1e-6
+  if case == "2d":
+    grid, pts, T = (320, 256), H.spiral_points(8, 40000), 3
+  elif case == "3d":
+    grid, pts, T = (64, 48, 80), H.uniform_points(300000, 3, 5), 2
+  elif case == "3d_sparse":
+    grid, pts, T = (128, 128, 128), H.stack_of_stars_points(25, 25, 128), 1
+  else:
+    grid, pts, T, cd, tol = (96, 120), H.uniform_points(40000, 2, 6, np.float64), 2, np.complex128, 1e-9
+  rank = len(grid)
+  M = pts.shape[0]
+  gate = max(2 * tol, 1e-6) if cd == np.complex64 else 2 * float(np.float32(tol))
+  for tt, sign, direction in ((2, -1, "forward"), (1, 1, "backward")):
+    src = H.random_complex((T, M) if tt == 1 else (T,) + grid, 101 + tt, cd)
+    out = nufft_ops._run_op(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid, f"type_{tt}", direction,
+                            tol, None, "nufft", engine_kwargs={"upsampling": 1}).cpu().numpy()
+    rp = ref.RefPlan(tt, list(grid[::-1]), sign, T, tol, cd, mode="lowups_direct", num_threads=NTHR)
+    assert rp.sigma == 1.25
+    rp.set_points(_plan_pts(pts))
+    want = rp.execute(src.reshape(T, -1))
+    rp.close()
+    err = H.rel_l2(out.reshape(T, -1), want)
+    assert err <= gate, f"sigma 1.25 {case} type {tt}: rel L2 {err:.3e} (ns {rp.kernel_width}, nf {rp.fine_dims})"
+
+
+def test_automatic_upsampling_follows_the_reference_rule():
+  """opts.upsampling = 2 reproduces PlanBase::set_default_options (nufft_plan.h:739-752): 1.25 for
+  large grids at tol >= 1e-9, else 2.0; the same kernel width and fine grid as the reference plan."""
+  ref = _ref()
+  from tensorflow_nufft_b200 import _lib
+  cases = [((512, 512), 1e-6, np.complex64), ((600, 600), 1e-6, np.complex64), ((128, 128, 128), 1e-6, np.complex64),
+           ((160, 160, 160), 1e-6, np.complex64), ((600, 600), 1e-10, np.complex128), ((600, 600), 1e-6, np.complex128),
+           ((256, 256, 256), 1e-5, np.complex64)]
+  for grid, tol, cd in cases:
+    rp = ref.RefPlan(2, list(grid[::-1]), -1, 1, tol, cd, mode="auto", num_threads=1)
+    plan = _lib.Plan(2, grid[::-1], -1, 1, float(np.float32(tol)), _lib.COMPLEX64 if cd == np.complex64 else _lib.COMPLEX128,
+                     device=0, upsampling=2, external_workspace=1)
+    info = plan.info()
+    assert info.upsampling_factor == rp.sigma, (grid, tol)
+    assert info.kernel_width == rp.kernel_width, (grid, tol)
+    assert list(info.fine_dims)[:len(grid)] == rp.fine_dims, (grid, tol)
+    assert abs(info.kernel_beta - rp.beta) <= 1e-6 * rp.beta
+    plan.close()
+    rp.close()

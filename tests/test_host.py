@@ -221,3 +221,12 @@ def test_point_set_reuse_is_opt_in_and_lives_in_the_c_library(L):
   assert _lib.plan_cache_stats()["idle"] == 0
   a, f = _lib.alloc_counts()
   assert a >= f >= 0
+
+
+def test_tf_glue_type_checks_against_reference_headers():
+  """The OpKernel-side glue is parsed and type-checked (g++ -fsyntax-only) against the reference's
+  nufft_plan.h and stand-in TF headers; skipped where the reference tree is absent (GPU box)."""
+  if not os.path.isdir("/root/reference/tensorflow_nufft"):
+    pytest.skip("reference tree not present")
+  import __graft_entry__ as g
+  g.check_tf_glue()
