@@ -18,7 +18,7 @@ def run(name, grid, pts, T, variants, reps=6, tol=1e-6):
     f = torch.zeros((T, N), dtype=torch.complex64, device="cuda")
     kw = dict(spread_method=v["method"], profile=1)
     if "bins" in v: kw["bin_dims"] = v["bins"]
-    for k in ("coils_per_cta", "max_subproblem_size", "no_pack", "no_tma_flush"):
+    for k in ("coils_per_cta", "max_subproblem_size", "no_pack", "no_tma_flush", "no_point_major"):
       if k in v: kw[k] = v[k]
     plan = _lib.Plan(1, grid[::-1], 1, T, tol, 0, device=0, **kw)
     st = torch.cuda.current_stream().cuda_stream
@@ -49,8 +49,8 @@ if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "prof":   # one variant, for ncu
     run("cfg2-spiral-512-T32", (512, 512), p, 32, [dict(method=6)], reps=3)
     sys.exit(0)
-  V = [dict(method=4), dict(method=6), dict(method=6, no_pack=1), dict(method=6, coils_per_cta=16),
-       dict(method=6, coils_per_cta=4), dict(method=6, no_tma_flush=1)]
+  V = [dict(method=4), dict(method=6), dict(method=6, no_point_major=1), dict(method=6, coils_per_cta=16),
+       dict(method=6, coils_per_cta=4), dict(method=6, no_pack=1), dict(method=6, coils_per_cta=16, no_point_major=1)]
   if not quick:
     V += [dict(method=6, bins=(16, 16)), dict(method=6, bins=(32, 8)), dict(method=6, coils_per_cta=16, bins=(32, 8)),
           dict(method=6, max_subproblem_size=256), dict(method=6, max_subproblem_size=4096)]

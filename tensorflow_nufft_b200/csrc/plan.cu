@@ -161,6 +161,7 @@ struct b200nufft_plan {
   DevBuf folded, keys0, keys1, vals0, vals1, hist, start, wrec;
   DevBuf bin_sizes, bin_start, num_sub, sub_start, sub_desc, misc;  // misc: scan tmp[1024] + sub_total + range flag
   DevBuf reuse;            // ReuseState (opts.reuse_points)
+  DevBuf ct;               // point-major strengths [M][batch] of the running batch (2D sweep spreader)
   MemCtx mem;
   int nb_max = 1;          // largest bin count over the geometries set_points may choose
   bool ws_bound = false;   // external workspace bound (opts.external_workspace)
@@ -198,7 +199,7 @@ struct b200nufft_plan {
   // buffers that live in the caller's workspace when one is bound
   std::vector<DevBuf*> ws_bufs() {
     return {&fine, &bin_sizes, &bin_start, &num_sub, &sub_start, &folded, &keys0, &keys1, &vals0, &vals1,
-            &hist, &start, &wrec, &sub_desc};
+            &hist, &start, &wrec, &sub_desc, &ct};
   }
 };
 
@@ -268,7 +269,7 @@ void points_bounds(const b200nufft_plan* p, F* lo, F* hi) {
   *lo = -ub;
 }
 
-constexpr int kNumWsBufs = 14;
+constexpr int kNumWsBufs = 15;
 // Bytes of every workspace-class buffer for point sets of up to M points, in ws_bufs() order.
 template <typename F>
 void ws_sizes(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
@@ -285,6 +286,7 @@ void ws_sizes(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
   out[11] = sizeof(int4) * m;
   out[12] = sizeof(F) * m * p->R;
   out[13] = sizeof(int4) * sub_bound;
+  out[14] = p->spread_method == 6 ? sizeof(Cplx<F>) * m * std::min(p->batch, p->ntransf) : 0;
 }
 void ws_sizes_any(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
   if (p->is_double) ws_sizes<double>(p, M, out); else ws_sizes<float>(p, M, out);
@@ -394,8 +396,9 @@ cudaError_t launch_spread_ws2(const b200nufft_plan* p, int ntr, const float2* c,
   return cudaGetLastError();
 }
 
+// pm != 0: c holds point-major strengths [M][ntr] (transpose_strengths_kernel), else coil-major [ntr][M]
 template <int Y>
-cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st, int pm) {
   GridGeom g = grid_geom(p);
   constexpr int NC = 4 * Y;
   const int ngroups = ntr / NC;
@@ -407,7 +410,8 @@ cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2
   const bool pack = p->opts.reserved[3] == 0;
 #define SWEEP_CASE(NS)                                                                            \
   case NS: {                                                                                     \
-    auto k = pack ? spread_sweep2d_f32_kernel<NS, Y, 1> : spread_sweep2d_f32_kernel<NS, Y, 0>;   \
+    auto k = pm ? (pack ? spread_sweep2d_f32_kernel<NS, Y, 1, 1> : spread_sweep2d_f32_kernel<NS, Y, 0, 1>)   \
+                : (pack ? spread_sweep2d_f32_kernel<NS, Y, 1, 0> : spread_sweep2d_f32_kernel<NS, Y, 0, 0>);  \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<static_cast<unsigned>(nblocks), 32, smem, st>>>(p->M, g, ngroups, p->sub_total(), p->sub_desc.as<int4>(), \
@@ -589,18 +593,29 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
     float2* ff = static_cast<float2*>(fw);
     const int nc_opt = p->opts.reserved[1];   // coils per CTA override (0 = auto)
     const int nc = nc_opt > 0 ? nc_opt : 8;
-    if (nc >= 16 && ntr % 16 == 0) e = launch_spread_sweep2d<4>(p, ntr, cc, ff, st);
-    else if (nc >= 8 && ntr % 8 == 0) e = launch_spread_sweep2d<2>(p, ntr, cc, ff, st);
-    else if (ntr % 4 == 0) e = launch_spread_sweep2d<1>(p, ntr, cc, ff, st);
-    else {
-      // coil counts that are not a multiple of 4: groups of 4 through the sweep kernel, the rest
-      // through the window-sorted kernel (same records, same sort)
-      const int main_n = ntr & ~3;
-      e = cudaSuccess;
-      if (main_n > 0) e = launch_spread_sweep2d<1>(p, main_n, cc, ff, st);
-      for (int k = main_n; k < ntr && e == cudaSuccess; ++k)
-        e = launch_spread_ws2<1>(p, 1, cc + static_cast<int64_t>(k) * p->M, ff + static_cast<int64_t>(k) * p->nftot, st);
+    // coil counts that are not a multiple of 4: groups of 4 through the sweep kernel, the rest
+    // through the window-sorted kernel (same records, same sort)
+    const int main_n = ntr & ~3;
+    e = cudaSuccess;
+    if (main_n > 0) {
+      // Strengths to point-major order [M][main_n] (reserved[7] = 1: off): the spreader then fetches
+      // the NC strengths of a point as ONE contiguous row piece (4 lanes x 16 bytes for 8 coils)
+      // instead of NC scattered 8-byte gathers through the sort permutation -- one cache line per
+      // point instead of NC.
+      const int pm = p->opts.reserved[7] == 0 ? 1 : 0;
+      const float2* src = cc;
+      if (pm) {
+        transpose_strengths_kernel<<<dim3(static_cast<unsigned>((p->M + 31) / 32), (main_n + 31) / 32), dim3(32, 8), 0, st>>>(
+            cc, p->ct.as<float2>(), p->M, main_n);
+        p->launches++;
+        src = p->ct.as<float2>();
+      }
+      if (nc >= 16 && main_n % 16 == 0) e = launch_spread_sweep2d<4>(p, main_n, src, ff, st, pm);
+      else if (nc >= 8 && main_n % 8 == 0) e = launch_spread_sweep2d<2>(p, main_n, src, ff, st, pm);
+      else e = launch_spread_sweep2d<1>(p, main_n, src, ff, st, pm);
     }
+    for (int k = main_n; k < ntr && e == cudaSuccess; ++k)
+      e = launch_spread_ws2<1>(p, 1, cc + static_cast<int64_t>(k) * p->M, ff + static_cast<int64_t>(k) * p->nftot, st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread sweep launch: %s", cudaGetErrorString(e));
   } else if (p->spread_method == 4) {
     cudaError_t e;

@@ -14,8 +14,10 @@
 //   * Points are sorted by (bin, window row, window column), so consecutive runs of a sweep are
 //     windows that move 2 cells to the right. The accumulators ROTATE instead of being flushed: the
 //     stage record holds the x-weights already rotated to the register slots (cell pair c lives in
-//     slot c & 3), so the inner loop has no phase, and a window step flushes only the ONE outgoing
-//     cell pair (a 128-bit read-modify-write per coil) instead of all four.
+//     slot c & 3), so the inner loop has no phase, and a window step moves only ONE cell pair: the
+//     outgoing pair is stored to the tile and the incoming pair's tile value is loaded as the new
+//     accumulator start (the accumulators have the tile's (re, im) layout: one 128-bit store and one
+//     128-bit load per coil, no adds, no dependent load-add-store chain).
 //   * Interior tiles leave through the TMA unit (cp.reduce.async.bulk.tensor add), as before.
 // The tile pitch is bin_x + 10 cells (= 2 mod 16), which makes the 8 row-lanes of a quarter warp
 // hit 8 distinct 16-byte bank groups.
@@ -41,9 +43,10 @@ template <int Y> struct SweepRec2 {
   static_assert((kStride / 4) % 2 == 1, "stage stride must be an odd multiple of 4 words");
 };
 
-// acc (cells a, b) += s * (wa, wb): one packed FFMA2 (fma.rn.f32x2), or two FFMA.
+// (re, im) += w * (cr, ci): one packed FFMA2 (fma.rn.f32x2; ptxas folds the {w, w} pack into the
+// instruction's scalar-broadcast operand form), or two FFMA.
 template <int PACK>
-__device__ __forceinline__ void fma_pair(float2& acc, float s, float2 w) {
+__device__ __forceinline__ void fma_cell(float& re, float& im, float w, float2 c) {
   if (PACK) {
     asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
         "mov.b64 ra, {%2, %2};\n\t"
@@ -51,28 +54,47 @@ __device__ __forceinline__ void fma_pair(float2& acc, float s, float2 w) {
         "mov.b64 rc, {%0, %1};\n\t"
         "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
         "mov.b64 {%0, %1}, rc;\n\t}"
-        : "+f"(acc.x), "+f"(acc.y) : "f"(s), "f"(w.x), "f"(w.y));
+        : "+f"(re), "+f"(im) : "f"(w), "f"(c.x), "f"(c.y));
   } else {
-    acc.x = fmaf(s, w.x, acc.x);
-    acc.y = fmaf(s, w.y, acc.y);
+    re = fmaf(w, c.x, re);
+    im = fmaf(w, c.y, im);
+  }
+}
+
+// c [T][M] -> c_pm [M][T] (complex64), 32 x 32 tiles through shared memory: both sides coalesced.
+__global__ void __launch_bounds__(256)
+transpose_strengths_kernel(const float2* __restrict__ c, float2* __restrict__ c_pm, int64_t M, int T) {
+  __shared__ float2 tile[32][33];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int t0 = blockIdx.y * 32;
+  for (int ty = threadIdx.y; ty < 32; ty += 8) {
+    const int t = t0 + ty;
+    const int64_t i = i0 + threadIdx.x;
+    if (t < T && i < M) tile[ty][threadIdx.x] = c[static_cast<int64_t>(t) * M + i];
+  }
+  __syncthreads();
+  for (int iy = threadIdx.y; iy < 32; iy += 8) {
+    const int64_t i = i0 + iy;
+    const int t = t0 + threadIdx.x;
+    if (t < T && i < M) c_pm[i * T + t] = tile[threadIdx.x][iy];
   }
 }
 
 template <int Y>
 inline size_t spread_sweep2d_smem_bytes(const int* bin) {
   const size_t ncell = static_cast<size_t>(bin[0] + kSweepHaloX) * (bin[1] + 8);
-  return 4 * Y * ncell * sizeof(float2) + 33 * SweepRec2<Y>::kStride * sizeof(float);
+  return 4 * Y * ncell * sizeof(float2) + 35 * SweepRec2<Y>::kStride * sizeof(float);
 }
 
 // One warp per (subproblem, group of NC = 4 Y coils). lane = g * 8 + r: r = row of the window,
 // g = coil sub-group (coils g * Y .. g * Y + Y - 1 of the CTA's group).
-template <int NS, int Y, int PACK>
+template <int NS, int Y, int PACK, int PM>
 __global__ void __launch_bounds__(32)
 spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restrict__ sub_total,
                           const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                           const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][4]*/,
-                          const float2* __restrict__ c, float2* __restrict__ fw,
-                          const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
+                          const float2* __restrict__ c_in /* PM: point-major [M][ngroups * NC], else [T][M] */,
+                          float2* __restrict__ fw, const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
   static_assert(NS <= 7, "8-cell windows");
   constexpr int NC = 4 * Y;
   using Rec = SweepRec2<Y>;
@@ -96,7 +118,7 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
   const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4;
   const int ncell = TX * TY;
   float4* tile4 = smem4;                                               // [NC][ncell / 2]
-  float* stage = reinterpret_cast<float*>(smem4 + NC * (ncell / 2));   // [BS + 1][SW]
+  float* stage = reinterpret_cast<float*>(smem4 + NC * (ncell / 2));   // [BS + 3][SW]
 
   for (int i = lane; i < NC * (ncell / 2); i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -106,15 +128,21 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
   // this lane's row r of coil (cg * Y + k): float4 index of cell pair 0 of tile row 0
   const int lane_tile4 = (cg * Y) * (ncell / 2) + r * (TX / 2);
 
-  const float2* ct = c + static_cast<int64_t>(t) * NC * M;
   float2* fwt = fw + static_cast<int64_t>(t) * NC * g.nftot;
+  // Strength rows: a point's NC strengths are NC * 8 contiguous bytes of c_pm; LPP lanes fetch one
+  // point (16 bytes each), so one load instruction covers PPI points and touches PPI cache lines.
+  constexpr int LPP = NC / 2;          // lanes per point
+  constexpr int PPI = 32 / LPP;        // points per load instruction
+  const int Ttot = ngroups * NC;
+  const float4* crow = reinterpret_cast<const float4*>(c_in + static_cast<int64_t>(t) * NC) + (lane % LPP);
+  const float2* ct = c_in + static_cast<int64_t>(t) * NC * M;   // !PM: coil-major strengths of this group
 
   // ---- register prefetch of this lane's point of the next batch ----
   float4 w4[4];
   int4 st_n = make_int4(0, 0, 0, 0);
-  float2 c_n[NC];
+  float4 c_n[LPP];   // c_n[q]: 16 bytes (2 coils) of point q * PPI + lane / LPP of the batch
 #pragma unroll
-  for (int k = 0; k < NC; ++k) c_n[k] = make_float2(0.f, 0.f);
+  for (int q = 0; q < LPP; ++q) c_n[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   int id_n2 = 0;
   auto fetch = [&](int bb) {
     const int pl = bb * BS + lane;
@@ -123,13 +151,26 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
 #pragma unroll
       for (int k = 0; k < 4; ++k) w4[k] = wrec4[j * 4 + k];
       st_n = start[j];
+    }
+    if (PM) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) c_n[k] = ct[static_cast<int64_t>(k) * M + id_n2];
+      for (int q = 0; q < LPP; ++q) {
+        const int pq = q * PPI + lane / LPP;                     // point of the batch this lane fetches a piece of
+        const int idq = __shfl_sync(0xffffffffu, id_n2, pq);
+        if (bb * BS + pq < np) c_n[q] = crow[static_cast<int64_t>(idq) * (Ttot / 2)];
+      }
+    } else if (pl < np) {   // coil-major: NC scattered 8-byte gathers for this lane's own point
+#pragma unroll
+      for (int q = 0; q < LPP; ++q) {
+        const float2 a = ct[static_cast<int64_t>(2 * q) * M + id_n2], b2 = ct[static_cast<int64_t>(2 * q + 1) * M + id_n2];
+        c_n[q] = make_float4(a.x, a.y, b2.x, b2.y);
+      }
     }
     const int pl2 = (bb + 1) * BS + lane;
     if (pl2 < np) id_n2 = idx[p0 + pl2];
   };
   int last_win = -2;
+  unsigned run_mask = 0;   // bit p: point p of the staged batch opens a new run (warp-uniform)
   auto stage_write = [&](int bb) {
     const int pl = bb * BS + lane;
     float* rec = stage + lane * SW;
@@ -145,6 +186,7 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
     const int prev = __shfl_up_sync(0xffffffffu, win, 1);
     const int flag = (lane == 0 ? (win != last_win) : (win != prev)) ? 1 : 0;
     last_win = __shfl_sync(0xffffffffu, win, BS - 1);
+    run_mask = __ballot_sync(0xffffffffu, flag);
     // x-weights rotated to their register slots: window cell pair i -> slot (wx_index + i) & 3
     const int rot = win & 3;
     if (win < 0) {   // dropped point: zero weights AND zero strengths (nothing, not even a NaN, reaches the tile)
@@ -161,55 +203,88 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
     rec4[3] = w4[3];
     rec4[4] = make_float4(__int_as_float((win << 1) | flag), 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < NC; k += 2)
-      rec4[5 + k / 2] = win >= 0 ? make_float4(c_n[k].x, c_n[k].y, c_n[k + 1].x, c_n[k + 1].y)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < LPP; ++q) {
+      if (PM) {
+        const int pq = q * PPI + lane / LPP;
+        const int wq = __shfl_sync(0xffffffffu, win, pq);          // dropped point: zero strengths
+        reinterpret_cast<float4*>(stage + pq * SW + Rec::kC)[lane % LPP] =
+            wq >= 0 ? c_n[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        rec4[5 + q] = win >= 0 ? c_n[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
   };
   if (lane < np) id_n2 = idx[p0 + lane];
   fetch(0);
 
-  // ---- accumulators: slot s = tile cell pair with (pair & 3) == s; per coil (re_a, re_b), (im_a, im_b) ----
-  float2 are[4][Y], aim[4][Y];
+  // ---- accumulators: slot s = the tile cell pair with (pair & 3) == s, held in the TILE's own layout
+  // (re_a, im_a, re_b, im_b) per coil, so that a slot moves to / from the tile with one 128-bit
+  // access and no arithmetic: a window step STORES the outgoing pair and LOADS the incoming one
+  // (whose tile value becomes the accumulator's start value) instead of read-add-write. ----
+  float4 acc[4][Y];
 #pragma unroll
   for (int sl = 0; sl < 4; ++sl)
 #pragma unroll
-    for (int k = 0; k < Y; ++k) { are[sl][k] = make_float2(0.f, 0.f); aim[sl][k] = make_float2(0.f, 0.f); }
+    for (int k = 0; k < Y; ++k) acc[sl][k] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cur_wx = 0, cur_wy = 0;
   bool have = false;
 
-  // adds the accumulators of slot SL to tile cell pair `pair` of this lane's row, and clears them
-  auto flush_slot = [&](auto sl_tag, int pair) {
+  auto store_slot = [&](auto sl_tag, int pair) {
     constexpr int SL = decltype(sl_tag)::value;
     float4* ptr = tile4 + lane_tile4 + cur_wy * TX + pair;   // row 2 * cur_wy + r: (2 cur_wy) * (TX / 2) = cur_wy * TX
+    if (row_ok) {
 #pragma unroll
-    for (int k = 0; k < Y; ++k) {
-      if (row_ok) {
-        float4 tv = ptr[k * (ncell / 2)];
-        tv.x += are[SL][k].x; tv.y += aim[SL][k].x; tv.z += are[SL][k].y; tv.w += aim[SL][k].y;
-        ptr[k * (ncell / 2)] = tv;
-      }
-      are[SL][k] = make_float2(0.f, 0.f);
-      aim[SL][k] = make_float2(0.f, 0.f);
+      for (int k = 0; k < Y; ++k) ptr[k * (ncell / 2)] = acc[SL][k];
     }
   };
-  auto flush_pair = [&](int pair) {
+  auto load_slot = [&](auto sl_tag, int pair) {
+    constexpr int SL = decltype(sl_tag)::value;
+    const float4* ptr = tile4 + lane_tile4 + cur_wy * TX + pair;
+    if (row_ok) {   // rows without weight keep their zero accumulators and are never stored
+#pragma unroll
+      for (int k = 0; k < Y; ++k) acc[SL][k] = ptr[k * (ncell / 2)];
+    }
+  };
+  auto store_pair = [&](int pair) {
     switch (pair & 3) {
-      case 0: flush_slot(std::integral_constant<int, 0>{}, pair); break;
-      case 1: flush_slot(std::integral_constant<int, 1>{}, pair); break;
-      case 2: flush_slot(std::integral_constant<int, 2>{}, pair); break;
-      default: flush_slot(std::integral_constant<int, 3>{}, pair); break;
+      case 0: store_slot(std::integral_constant<int, 0>{}, pair); break;
+      case 1: store_slot(std::integral_constant<int, 1>{}, pair); break;
+      case 2: store_slot(std::integral_constant<int, 2>{}, pair); break;
+      default: store_slot(std::integral_constant<int, 3>{}, pair); break;
     }
   };
-  // a run with window `win` starts: retire the cell pairs the open window leaves behind
-  auto open_window = [&](int win) {
-    if (have) {
-      int n = 4;
-      if (win >= 0 && (win / kWinStride) == cur_wy) n = min(4, (win % kWinStride) - cur_wx);
-      for (int i = 0; i < n; ++i) flush_pair(cur_wx + i);
-      __syncwarp();
+  auto load_pair = [&](int pair) {
+    switch (pair & 3) {
+      case 0: load_slot(std::integral_constant<int, 0>{}, pair); break;
+      case 1: load_slot(std::integral_constant<int, 1>{}, pair); break;
+      case 2: load_slot(std::integral_constant<int, 2>{}, pair); break;
+      default: load_slot(std::integral_constant<int, 3>{}, pair); break;
     }
+  };
+  // A run with window `win` starts (-1: none). Same sweep (same window row): the window moved d
+  // pairs to the right; the d outgoing pairs go back to the tile, the d incoming ones are loaded.
+  // New sweep: all four pairs are stored, and the new window's four pairs are loaded after a warp
+  // barrier (another lane owned those tile rows in the previous sweep).
+  auto open_window = [&](int win) {
+    const int nwx = win % kWinStride, nwy = win / kWinStride;
+    const bool same_sweep = have && win >= 0 && nwy == cur_wy;
+    if (same_sweep) {
+      const int d = min(4, nwx - cur_wx);
+      for (int i = 0; i < d; ++i) store_pair(cur_wx + i);
+      for (int i = 0; i < d; ++i) load_pair(nwx + 4 - d + i);
+      cur_wx = nwx;
+      return;
+    }
+    if (have) {
+      for (int i = 0; i < 4; ++i) store_pair(cur_wx + i);
+    }
+    __syncwarp();
     have = win >= 0;
-    if (have) { cur_wx = win % kWinStride; cur_wy = win / kWinStride; }
+    if (have) {
+      cur_wx = nwx;
+      cur_wy = nwy;
+      for (int i = 0; i < 4; ++i) load_pair(cur_wx + i);
+    }
   };
 
   const int nbatch = (np + BS - 1) / BS;
@@ -219,42 +294,58 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
     if (bb + 1 < nbatch) fetch(bb + 1);
 
     const int cnt = min(BS, np - bb * BS);
-    // The stage holds BS + 1 records so that the prefetch of point p + 1 never needs a guard.
-    float4 wxa = *reinterpret_cast<const float4*>(stage);
-    float4 wxb = *reinterpret_cast<const float4*>(stage + 4);
-    float wy = stage[Rec::kWy + r];
-    int hdr = __float_as_int(stage[Rec::kHdr]);
-    float2 cc[Y];
+    // Three points in flight: the shared-memory loads of point p + 3 are issued right after point p
+    // has been consumed, two points (~45 instructions) ahead of their first use; with 7 one-warp
+    // CTAs per SM nothing else hides the load latency. The stage holds BS + 3 records so that the
+    // look-ahead never needs a guard. The run flags travel as a ballot mask, the header word is
+    // read only when a run starts.
+    struct PRec { float4 xa, xb; float wy; float2 cc[Y]; };
+    auto ld = [&](PRec& R, int p) {
+      const float* rec = stage + p * SW;
+      R.xa = *reinterpret_cast<const float4*>(rec);
+      R.xb = *reinterpret_cast<const float4*>(rec + 4);
+      R.wy = rec[Rec::kWy + r];
+      if (Y == 2) {
+        const float4 c4 = *reinterpret_cast<const float4*>(rec + Rec::kC + 4 * cg);
+        R.cc[0] = make_float2(c4.x, c4.y);
+        R.cc[Y - 1] = make_float2(c4.z, c4.w);
+      } else {
 #pragma unroll
-    for (int k = 0; k < Y; ++k) cc[k] = *reinterpret_cast<const float2*>(stage + Rec::kC + 2 * (cg * Y + k));
-#pragma unroll 2
-    for (int p = 0; p < cnt; ++p) {
-      const float* nxt = stage + (p + 1) * SW;
-      const float4 xa = wxa, xb = wxb;
-      const float wy_c = wy;
-      const int hdr_c = hdr;
-      float2 cc_c[Y];
-#pragma unroll
-      for (int k = 0; k < Y; ++k) cc_c[k] = cc[k];
-      wxa = *reinterpret_cast<const float4*>(nxt);
-      wxb = *reinterpret_cast<const float4*>(nxt + 4);
-      wy = nxt[Rec::kWy + r];
-      hdr = __float_as_int(nxt[Rec::kHdr]);
-#pragma unroll
-      for (int k = 0; k < Y; ++k) cc[k] = *reinterpret_cast<const float2*>(nxt + Rec::kC + 2 * (cg * Y + k));
-      if (hdr_c & 1) open_window(hdr_c >> 1);   // warp-uniform
+        for (int k = 0; k < Y; ++k) R.cc[k] = *reinterpret_cast<const float2*>(rec + Rec::kC + 2 * (cg * Y + k));
+      }
+    };
+    auto comp = [&](const PRec& R, int p) {
+      if ((run_mask >> p) & 1u) open_window(__float_as_int(stage[p * SW + Rec::kHdr]) >> 1);   // warp-uniform
 #pragma unroll
       for (int k = 0; k < Y; ++k) {
-        const float cre = cc_c[k].x * wy_c, cim = cc_c[k].y * wy_c;
-        fma_pair<PACK>(are[0][k], cre, make_float2(xa.x, xa.y));
-        fma_pair<PACK>(aim[0][k], cim, make_float2(xa.x, xa.y));
-        fma_pair<PACK>(are[1][k], cre, make_float2(xa.z, xa.w));
-        fma_pair<PACK>(aim[1][k], cim, make_float2(xa.z, xa.w));
-        fma_pair<PACK>(are[2][k], cre, make_float2(xb.x, xb.y));
-        fma_pair<PACK>(aim[2][k], cim, make_float2(xb.x, xb.y));
-        fma_pair<PACK>(are[3][k], cre, make_float2(xb.z, xb.w));
-        fma_pair<PACK>(aim[3][k], cim, make_float2(xb.z, xb.w));
+        const float2 cw = make_float2(R.cc[k].x * R.wy, R.cc[k].y * R.wy);
+        // cell (re, im) += w_cell * (Re, Im)(c wy): packed FFMA2 with a scalar-broadcast weight
+        fma_cell<PACK>(acc[0][k].x, acc[0][k].y, R.xa.x, cw);
+        fma_cell<PACK>(acc[0][k].z, acc[0][k].w, R.xa.y, cw);
+        fma_cell<PACK>(acc[1][k].x, acc[1][k].y, R.xa.z, cw);
+        fma_cell<PACK>(acc[1][k].z, acc[1][k].w, R.xa.w, cw);
+        fma_cell<PACK>(acc[2][k].x, acc[2][k].y, R.xb.x, cw);
+        fma_cell<PACK>(acc[2][k].z, acc[2][k].w, R.xb.y, cw);
+        fma_cell<PACK>(acc[3][k].x, acc[3][k].y, R.xb.z, cw);
+        fma_cell<PACK>(acc[3][k].z, acc[3][k].w, R.xb.w, cw);
       }
+    };
+    PRec A, B, C;
+    ld(A, 0);
+    ld(B, 1);
+    ld(C, 2);
+    int p = 0;
+    for (; p + 3 <= cnt; p += 3) {
+      comp(A, p);
+      ld(A, p + 3);
+      comp(B, p + 1);
+      ld(B, p + 4);
+      comp(C, p + 2);
+      ld(C, p + 5);
+    }
+    if (p < cnt) {
+      comp(A, p);
+      if (p + 1 < cnt) comp(B, p + 1);
     }
     __syncwarp();
   }
