@@ -168,7 +168,7 @@ class Dist:
 
 def kernel_name(ttype, rank):
   if ttype == 1:
-    return "spread_ws2_f32_kernel" if rank == 2 else "spread_tile_f32_kernel"
+    return "spread_sweep2d_f32_kernel" if rank == 2 else "spread_sweep3d_f32_kernel"
   return "interp_qw_f32_kernel"
 
 

@@ -78,9 +78,10 @@ typedef struct b200nufft_opts {
   int bin_dims[3];         /* engine bin geometry (cf. InternalOptions::gpu_bin_size); 0 = auto   */
   int max_subproblem_size; /* points per subproblem (cf. gpu_max_subproblem_size = 1024); 0 = auto */
   int spread_method;       /* 0 auto, 1 global-atomic point-driven, 2 shared-memory tiles,
-                              3 window-sorted register runs, 4 same with even-row windows, 6 window
-                              swept along x with rotating row accumulators (4 and 6: 2D type-1
-                              NUFFT plans; they fall back to 3 elsewhere)                         */
+                              3 window-sorted register runs, 4 same with even-row windows, 6 / 7 window
+                              swept along x with rotating row accumulators in 2D / 3D (7 streams the
+                              tile through an 8-plane ring). 4, 6, 7: type-1 NUFFT plans only; they
+                              fall back to 3 / 2 elsewhere                                        */
   int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged),
                               lanes over one point's stencil, 3 shared-memory tiles, quarter warp
                               per point                                                           */

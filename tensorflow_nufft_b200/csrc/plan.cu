@@ -140,6 +140,7 @@ struct b200nufft_plan {
   bool zrange_valid = false;   // sub_desc.w holds the z extent of every subproblem (3D interp plans)
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
+  bool ws3 = false;        // 3D sweep spreader: even-aligned windows in x, y and z, (bin, wz, wy, wx) keys
   size_t tile_smem = 0;
 
   // device state
@@ -426,6 +427,33 @@ cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2
   return cudaGetLastError();
 }
 
+cudaError_t launch_spread_sweep3d(const b200nufft_plan* p, int ntr, const float2* c, float2* fw, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  const int64_t nblocks = p->sub_bound * ntr;
+  if (nblocks > 2147483647LL) return cudaErrorInvalidValue;
+  const size_t smem = spread_sweep3d_smem_bytes(p->bin);
+  // one-plane TMA boxes: the planes are (bin_x + 10) * (bin_y + 8) * 8 bytes = a multiple of 128
+  const bool plane_ok = ((p->bin[0] + kSweepHaloX) * (p->bin[1] + 8) * sizeof(float2)) % 128 == 0;
+  const int use_tma = (p->opts.reserved[5] == 0 && plane_ok &&
+                       ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, 1, kSweepHaloX)) ? 1 : 0;
+  const bool pack = p->opts.reserved[3] == 0;
+#define SWEEP3_CASE(NS)                                                                          \
+  case NS: {                                                                                     \
+    auto k = pack ? spread_sweep3d_f32_kernel<NS, 1> : spread_sweep3d_f32_kernel<NS, 0>;         \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<static_cast<unsigned>(nblocks), 32, smem, st>>>(p->M, g, ntr, p->sub_total(), p->sub_desc.as<int4>(), \
+                              p->idx, p->start.as<int4>(), p->wrec.as<float4>(), c, fw, p->tmap_out.map, use_tma); \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    SWEEP3_CASE(2) SWEEP3_CASE(3) SWEEP3_CASE(4) SWEEP3_CASE(5) SWEEP3_CASE(6) SWEEP3_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef SWEEP3_CASE
+  return cudaGetLastError();
+}
+
 // Builds (or reuses) the TMA tensor map of a fine-grid batch [ntr][nf2][nf1][2*nf0] float32 with a
 // box of one tile. cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -587,6 +615,9 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
   if (p->spread_method == 5) {
     cudaError_t e = launch_spread_rowlane<F>(p, ntr, static_cast<const Cplx<F>*>(c), static_cast<Cplx<F>*>(fw), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread rowlane launch: %s", cudaGetErrorString(e));
+  } else if (p->spread_method == 7) {
+    cudaError_t e = launch_spread_sweep3d(p, ntr, static_cast<const float2*>(c), static_cast<float2*>(fw), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "spread sweep3d launch: %s", cudaGetErrorString(e));
   } else if (p->spread_method == 6) {
     cudaError_t e;
     const float2* cc = static_cast<const float2*>(c);
@@ -881,8 +912,11 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.WX = p->bin[0] / 2 + 3;
   bg.WY = p->ws2 ? p->bin[1] / 2 + 3 : p->bin[1] + 7;
   bg.align_x = p->is_double ? 0 : 1;
-  bg.align_y = p->ws2 ? 1 : 0;
-  const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY : 1);
+  bg.align_y = (p->ws2 || p->ws3) ? 1 : 0;
+  if (p->ws3) bg.WY = p->bin[1] / 2 + 3;
+  bg.align_z = p->ws3 ? 1 : 0;
+  bg.WZ = p->ws3 ? p->bin[2] / 2 + 3 : 1;
+  const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY * bg.WZ : 1);
 
   if (skip) {
     clear_ints_kernel<<<grid_for(p->nbtot + 1, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot + 1, skip);
@@ -942,7 +976,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   LAUNCH_OK(p);
 
   const int align_x = (!p->is_double) ? 1 : 0;
-  const int align = align_x | (p->ws2 ? 2 : 0);
+  const int align = align_x | ((p->ws2 || p->ws3) ? 2 : 0) | (p->ws3 ? 4 : 0);
   if (p->PX == 8 && p->PY == 8 && rank >= 2) {
     const F beta = static_cast<F>(p->kp.beta), cc = static_cast<F>(p->kp.c), hw = static_cast<F>(p->kp.half_width);
     if (rank == 2)
@@ -952,7 +986,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     else
       stencil_record8_kernel<F, 3><<<grid_for(M * 3, 256, 16), 256, 0, st>>>(
           M, p->idx, p->folded.as<F>(), p->kp.ns, beta, cc, hw,
-          align_x, p->start.as<int>(), p->wrec.as<F>(), skip);
+          p->ws3 ? align : align_x, p->start.as<int>(), p->wrec.as<F>(), skip);
   } else {
     stencil_record_kernel<F><<<grid_for(M, std::max(1, 256 / p->R), 16), dim3(p->R, std::max(1, 256 / p->R)), 0, st>>>(
         M, rank, p->idx, p->folded.as<F>(), p->kp.ns,
@@ -1050,7 +1084,9 @@ int create_impl(b200nufft_plan* p) {
   // 3 for spread-only plans); 3D -> plane-owner tile kernel (2)
   // (measured on B200, cfg2 per 32 coils: 1.38 ms (4) vs 1.70 ms (3) vs 4.5 ms (2); cfg3: 3.2 ms
   //  tile vs >= 4.0 ms window-sorted)
-  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 6 : 2) : 1) : p->opts.spread_method;
+  // (round 2: sweep spreaders 6 / 7 -- cfg2 0.96 ms vs 1.29 (4); cfg3 1.32 ms vs 2.36 (2); cfg4's point set as
+  //  type 1: 1.63 ms vs 1.97 (2))
+  p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 6 : 7) : 1) : p->opts.spread_method;
   // interpolator: 3 = quarter-warp gather (measured: cfg2-type2 0.56 vs 0.92 ms per 8 coils, cfg3-type2
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
@@ -1068,7 +1104,9 @@ int create_impl(b200nufft_plan* p) {
   // ws2 (4) and the sweep spreader (6) are 2D, type-1 NUFFT plans only (their records carry a row shift)
   if ((p->spread_method == 4 || p->spread_method == 6) && (p->rank != 2 || p->type != 1 || p->opts.spread_only))
     p->spread_method = 3;
-  const bool ws_any = p->spread_method == 3 || p->spread_method == 4 || p->spread_method == 6;
+  // 7: 3D sweep spreader (type-1 NUFFT plans; its records carry y and z shifts)
+  if (p->spread_method == 7 && (p->rank != 3 || p->type != 1 || p->opts.spread_only || !tile_ok)) p->spread_method = tile_ok ? 2 : 1;
+  const bool ws_any = p->spread_method == 3 || p->spread_method == 4 || p->spread_method == 6 || p->spread_method == 7;
   int def_bin[3] = {1, 1, 1};
   if (p->rank == 1) { def_bin[0] = 1024; }
   else if (p->rank == 2) {
@@ -1086,6 +1124,7 @@ int create_impl(b200nufft_plan* p) {
     if (p->type == 1 && p->spread_method == 3) def_bin[1] = 8;
     if (p->type == 2 && p->interp_method == 3) def_bin[1] = 8;   // cfg3-type2 1.18 vs 1.35 ms at 16 x 16 x 2
     if (p->type == 1 && p->spread_method == 2) def_bin[1] = 8;   // cfg3 2.79 vs 3.01 ms at 16 x 16 x 2 (TMA flush)
+    if (p->type == 1 && p->spread_method == 7) { def_bin[1] = 8; def_bin[2] = 16; }   // ring of 8 planes: depth is free
   }
   p->nbtot = 1;
   for (int d = 0; d < 3; ++d) {
@@ -1103,13 +1142,17 @@ int create_impl(b200nufft_plan* p) {
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && ws_any;
   p->ws2 = p->ws && (p->spread_method == 4 || p->spread_method == 6);
+  p->ws3 = p->ws && p->spread_method == 7;
+  if (p->ws3 && ((p->bin[1] & 1) || (p->bin[2] & 1)))
+    return set_err(p, B200NUFFT_INVALID_ARGUMENT, "3D sweep spreader needs even bin_dims[1] and bin_dims[2]");
   if (p->ws2 && (p->bin[1] & 1))
     return set_err(p, B200NUFFT_INVALID_ARGUMENT, "even-row window spreader needs an even bin_dims[1]");
-  if (p->ws && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)
+  if (p->ws && !p->ws3 && p->rank == 3 && p->bin[2] != 4 && p->bin[2] != 8)
     return set_err(p, B200NUFFT_INVALID_ARGUMENT, "window-sorted 3D spreader needs bin_dims[2] of 4 or 8");
-  if (p->ws && static_cast<int64_t>(p->nbtot) * (p->bin[0] / 2 + 3) * (p->bin[1] + 7) >= (int64_t(1) << 31)) {
+  if (p->ws && static_cast<int64_t>(p->nbtot) * (p->bin[0] / 2 + 3) * (p->bin[1] + 7) * (p->ws3 ? p->bin[2] / 2 + 3 : 1) >= (int64_t(1) << 31)) {
     p->ws = false;
     p->ws2 = false;
+    p->ws3 = false;
     p->spread_method = 2;
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
@@ -1125,6 +1168,7 @@ int create_impl(b200nufft_plan* p) {
       return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
     size_t need = 0;
     if (uses_tile && p->spread_method == 6) need = std::max(need, spread_sweep2d_smem_bytes<4>(p->bin));
+    else if (uses_tile && p->spread_method == 7) need = std::max(need, spread_sweep3d_smem_bytes(p->bin));
     else if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
     if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin, 8) : interp_qw_smem_bytes<3>(p->bin));

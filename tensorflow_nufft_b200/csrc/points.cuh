@@ -65,6 +65,8 @@ struct BinGeom {
   int WX, WY;
   int align_x;   // stencil x start aligned down to an even cell
   int align_y;   // stencil y start aligned down to an even row (ws2 spreader): wy counts row pairs
+  int align_z;   // 3D sweep spreader: z start aligned down to an even plane, key also carries the z window
+  int WZ;
 };
 
 template <typename F>
@@ -130,6 +132,12 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
       if (g.align_y) wy = (i1y - (i1y & 1) - (bd[1] * g.bin[1] - 4)) >> 1;
       wx = wx < 0 ? 0 : (wx >= g.WX ? g.WX - 1 : wx);
       wy = wy < 0 ? 0 : (wy >= g.WY ? g.WY - 1 : wy);
+      if (g.align_z) {   // 3D sweep: (bin, window z, window y, window x)
+        const int i1z = static_cast<int>(ceil(sub_rn(x[2], half_width)));
+        int wz = (i1z - (i1z & 1) - (bd[2] * g.bin[2] - 4)) >> 1;
+        wz = wz < 0 ? 0 : (wz >= g.WZ ? g.WZ - 1 : wz);
+        key = key * g.WZ + wz;
+      }
       key = key * (g.WX * g.WY) + wy * g.WX + wx;
     }
     // one 16 / 32-byte record per point: the record kernel gathers a point's coordinates through

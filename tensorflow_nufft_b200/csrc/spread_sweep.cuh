@@ -229,61 +229,55 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
   int cur_wx = 0, cur_wy = 0;
   bool have = false;
 
-  auto store_slot = [&](auto sl_tag, int pair) {
-    constexpr int SL = decltype(sl_tag)::value;
-    float4* ptr = tile4 + lane_tile4 + cur_wy * TX + pair;   // row 2 * cur_wy + r: (2 cur_wy) * (TX / 2) = cur_wy * TX
-    if (row_ok) {
-#pragma unroll
-      for (int k = 0; k < Y; ++k) ptr[k * (ncell / 2)] = acc[SL][k];
-    }
-  };
-  auto load_slot = [&](auto sl_tag, int pair) {
-    constexpr int SL = decltype(sl_tag)::value;
-    const float4* ptr = tile4 + lane_tile4 + cur_wy * TX + pair;
-    if (row_ok) {   // rows without weight keep their zero accumulators and are never stored
-#pragma unroll
-      for (int k = 0; k < Y; ++k) acc[SL][k] = ptr[k * (ncell / 2)];
-    }
-  };
-  auto store_pair = [&](int pair) {
-    switch (pair & 3) {
-      case 0: store_slot(std::integral_constant<int, 0>{}, pair); break;
-      case 1: store_slot(std::integral_constant<int, 1>{}, pair); break;
-      case 2: store_slot(std::integral_constant<int, 2>{}, pair); break;
-      default: store_slot(std::integral_constant<int, 3>{}, pair); break;
-    }
-  };
-  auto load_pair = [&](int pair) {
-    switch (pair & 3) {
-      case 0: load_slot(std::integral_constant<int, 0>{}, pair); break;
-      case 1: load_slot(std::integral_constant<int, 1>{}, pair); break;
-      case 2: load_slot(std::integral_constant<int, 2>{}, pair); break;
-      default: load_slot(std::integral_constant<int, 3>{}, pair); break;
-    }
-  };
+  // Slot sl holds the tile cell pair P in [wx, wx + 4) with (P & 3) == sl.
+  auto pair_of = [](int wx, int sl) { return wx + ((sl - wx) & 3); };
+  float4* rowp = tile4 + lane_tile4;   // this lane's row of the open sweep, coil k at rowp[k * (ncell / 2) + pair]
   // A run with window `win` starts (-1: none). Same sweep (same window row): the window moved d
-  // pairs to the right; the d outgoing pairs go back to the tile, the d incoming ones are loaded.
-  // New sweep: all four pairs are stored, and the new window's four pairs are loaded after a warp
-  // barrier (another lane owned those tile rows in the previous sweep).
+  // pairs to the right; every slot computes which pair it holds and whether that pair leaves the
+  // window -- then it is stored and the pair of the new window that takes the slot is loaded
+  // (predicated 128-bit accesses, no branch on the slot index). New sweep: all four pairs are
+  // stored, and the new window's four pairs are loaded after a warp barrier (another lane owned
+  // those tile rows in the previous sweep).
   auto open_window = [&](int win) {
     const int nwx = win % kWinStride, nwy = win / kWinStride;
-    const bool same_sweep = have && win >= 0 && nwy == cur_wy;
-    if (same_sweep) {
-      const int d = min(4, nwx - cur_wx);
-      for (int i = 0; i < d; ++i) store_pair(cur_wx + i);
-      for (int i = 0; i < d; ++i) load_pair(nwx + 4 - d + i);
+    if (have && win >= 0 && nwy == cur_wy) {
+      const int d = nwx - cur_wx;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int P = pair_of(cur_wx, sl);
+        if (row_ok && P - cur_wx < d) {
+          const int Q = pair_of(nwx, sl);
+#pragma unroll
+          for (int k = 0; k < Y; ++k) {
+            rowp[k * (ncell / 2) + P] = acc[sl][k];
+            acc[sl][k] = rowp[k * (ncell / 2) + Q];
+          }
+        }
+      }
       cur_wx = nwx;
       return;
     }
-    if (have) {
-      for (int i = 0; i < 4; ++i) store_pair(cur_wx + i);
+    if (have && row_ok) {
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int P = pair_of(cur_wx, sl);
+#pragma unroll
+        for (int k = 0; k < Y; ++k) rowp[k * (ncell / 2) + P] = acc[sl][k];
+      }
     }
     __syncwarp();
     have = win >= 0;
-    if (have) {
-      cur_wx = nwx;
-      cur_wy = nwy;
-      for (int i = 0; i < 4; ++i) load_pair(cur_wx + i);
+    if (!have) return;
+    cur_wx = nwx;
+    cur_wy = nwy;
+    rowp = tile4 + lane_tile4 + cur_wy * TX;   // row 2 * cur_wy + r: (2 cur_wy) * (TX / 2) = cur_wy * TX
+    if (row_ok) {   // rows without weight keep their zero accumulators and are never stored
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int P = pair_of(cur_wx, sl);
+#pragma unroll
+        for (int k = 0; k < Y; ++k) acc[sl][k] = rowp[k * (ncell / 2) + P];
+      }
     }
   };
 
@@ -379,6 +373,288 @@ spread_sweep2d_f32_kernel(int64_t M, GridGeom g, int ngroups, const int* __restr
       red_add(reinterpret_cast<float4*>(fwt + static_cast<int64_t>(k) * g.nftot + cell), tv);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D: the same sweep with one coil per CTA. lane = zg * 8 + r: r = row (y) of the 8 x 8 x 8 window
+// (even-aligned in all three dimensions: the record kernel shifts and zero-pads wx, wy AND wz),
+// zg = pair of z-planes (2 zg, 2 zg + 1). A lane holds 8 x-cells x 2 planes = 32 accumulator floats,
+// rotating along x. Points are sorted by (bin, window z, window y, window x); a sweep is a run of
+// windows with the same (z, y). Per point: 2 x LDS.128 (x-weights, warp-uniform), y-weight, the
+// lane's two z-weights (LDS.64), the strength (LDS.64), 6 FMUL, 16 FFMA2 -- against a 128-bit
+// read-modify-write of the shared-memory tile per lane and z-plane in spread.cuh (7 per point).
+// ------------------------------------------------------------------------------------------------
+struct SweepRec3 {
+  // words: [0..7] x-weights rotated to slots, [8..15] wy, [16..23] wz, [24] header, [26..27] strength
+  static constexpr int kWy = 8, kWz = 16, kHdr = 24, kC = 26;
+  static constexpr int kStride = 28;   // 4 * 7 words: conflict-free staging
+};
+
+constexpr int kSweepRing = 8;   // z-planes of the tile resident in shared memory (one window depth)
+
+inline size_t spread_sweep3d_smem_bytes(const int* bin) {
+  const size_t plane = static_cast<size_t>(bin[0] + kSweepHaloX) * (bin[1] + 8);
+  return kSweepRing * plane * sizeof(float2) + 35 * SweepRec3::kStride * sizeof(float);
+}
+
+// Z-SLAB STREAMING: the sort order is (bin, window z, window y, window x), so the window's z start
+// never decreases inside a subproblem. Shared memory therefore holds only a RING of 8 z-planes of
+// the (bin + halo) tile -- the planes the current window depth [2 wz, 2 wz + 8) covers -- instead
+// of all bin_z + 8: when wz advances, the planes left behind are complete, leave through the TMA
+// unit (one reduce-add per plane) and are cleared for reuse. 27 KB per one-warp CTA instead of 53,
+// i.e. 7 resident warps per SM instead of 4 (the kernel is latency-bound), whatever the bin depth.
+template <int NS, int PACK>
+__global__ void __launch_bounds__(32)
+spread_sweep3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__ sub_total,
+                          const int4* __restrict__ sub_desc, const int* __restrict__ idx,
+                          const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][6]*/,
+                          const float2* __restrict__ c, float2* __restrict__ fw,
+                          const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
+  static_assert(NS <= 7, "8-cell windows");
+  using Rec = SweepRec3;
+  constexpr int SW = Rec::kStride;
+  constexpr int BS = 32;
+  constexpr int kWinStride = 64;   // window id = (wz * 64 + wy) * 64 + wx
+  constexpr int RING = kSweepRing;
+  extern __shared__ __align__(128) float4 smem4[];
+
+  const int s = blockIdx.x / ntr;
+  const int t = blockIdx.x - s * ntr;
+  const int nsub_live = *sub_total;
+  const int4 sd = sub_desc[s];
+  if (s >= nsub_live) return;
+  const int lane = threadIdx.x;
+  const int b = sd.x, p0 = sd.y, np = sd.z;
+
+  const int TX = g.bin[0] + kSweepHaloX, TY = g.bin[1] + 8, TZ = g.bin[2] + 8;
+  const int bx = b % g.nbins[0];
+  const int by = (b / g.nbins[0]) % g.nbins[1];
+  const int bz = b / (g.nbins[0] * g.nbins[1]);
+  const int ox = bx * g.bin[0] - 4, oy = by * g.bin[1] - 4, oz = bz * g.bin[2] - 4;
+  const int plane4 = TX * TY / 2;   // float4 per z-plane
+  float4* tile4 = smem4;            // [RING][plane4]: tile plane z lives in ring slot z & 7
+  float* stage = reinterpret_cast<float*>(smem4 + RING * plane4);   // [BS + 3][SW]
+  const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
+                        oz >= 0 && oz + TZ <= g.nf[2];
+
+  for (int i = lane; i < RING * plane4; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int r = lane & 7;
+  const int zg = lane >> 3;
+  const bool ok0 = r < NS + 1 && 2 * zg < NS + 1, ok1 = r < NS + 1 && 2 * zg + 1 < NS + 1;
+  const int lane_row4 = r * (TX / 2);
+
+  const float2* ct = c + static_cast<int64_t>(t) * M;
+  float2* fwt = fw + static_cast<int64_t>(t) * g.nftot;
+
+  // ---- register prefetch of this lane's point of the next batch ----
+  float4 w4[6];
+  int4 st_n = make_int4(0, 0, 0, 0);
+  float2 c_n = make_float2(0.f, 0.f);
+  int id_n2 = 0;
+  auto fetch = [&](int bb) {
+    const int pl = bb * BS + lane;
+    if (pl < np) {
+      const int64_t j = p0 + pl;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w4[k] = wrec4[j * 6 + k];
+      st_n = start[j];
+      c_n = ct[id_n2];
+    }
+    const int pl2 = (bb + 1) * BS + lane;
+    if (pl2 < np) id_n2 = idx[p0 + pl2];
+  };
+  int last_win = -2;
+  unsigned run_mask = 0;
+  auto stage_write = [&](int bb) {
+    const int pl = bb * BS + lane;
+    float* rec = stage + lane * SW;
+    int win = -1;
+    if (pl < np) {
+      const int rx = st_n.x - ox, ry = st_n.y - oy, rz = st_n.z - oz;
+      // Memory safety for coordinates outside the declared points_range (see the 2D kernel).
+      const bool fits = rx >= 0 && rx + 8 <= TX && ry >= 0 && ry + NS + 1 <= TY && rz >= 0 && rz + NS + 1 <= TZ &&
+                        ((rx | ry | rz) & 1) == 0;
+      if (fits) win = ((rz >> 1) * kWinStride + (ry >> 1)) * kWinStride + (rx >> 1);
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, win, 1);
+    const int flag = (lane == 0 ? (win != last_win) : (win != prev)) ? 1 : 0;
+    last_win = __shfl_sync(0xffffffffu, win, BS - 1);
+    run_mask = __ballot_sync(0xffffffffu, flag);
+    const int rot = win & 3;
+    if (win < 0) {
+      w4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      c_n = make_float2(0.f, 0.f);
+    }
+    float2* wxs = reinterpret_cast<float2*>(rec);
+    wxs[(rot + 0) & 3] = make_float2(w4[0].x, w4[0].y);
+    wxs[(rot + 1) & 3] = make_float2(w4[0].z, w4[0].w);
+    wxs[(rot + 2) & 3] = make_float2(w4[1].x, w4[1].y);
+    wxs[(rot + 3) & 3] = make_float2(w4[1].z, w4[1].w);
+    float4* rec4 = reinterpret_cast<float4*>(rec);
+    rec4[2] = w4[2];
+    rec4[3] = w4[3];
+    rec4[4] = w4[4];
+    rec4[5] = w4[5];
+    rec4[6] = make_float4(__int_as_float((win << 1) | flag), 0.f, c_n.x, c_n.y);
+  };
+  if (lane < np) id_n2 = idx[p0 + lane];
+  fetch(0);
+
+  // ---- accumulators: [slot][plane], tile layout (re_a, im_a, re_b, im_b) ----
+  float4 acc[4][2];
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) { acc[sl][0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[sl][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  int cur_wx = 0, cur_wy = 0, cur_wz = -1;
+  int zbase = -1;           // tile planes [zbase, zbase + 8) are resident (zbase = 2 * window z of the open depth)
+  float4* row0 = tile4;     // this lane's row in its two planes of the open window: row0[pair], row1[pair]
+  float4* row1 = tile4;
+  bool have = false;
+
+  // Retires the tile planes [z0, z1): adds them to the fine grid and clears their ring slots.
+  auto retire_planes = [&](int z0, int z1) {
+    if (z1 <= z0) return;
+    __syncwarp();
+    if (interior) {
+      fence_proxy_async_smem();   // every lane: its generic-proxy tile writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        for (int z = z0; z < z1; ++z) tma_reduce_add_4d(&tmap_out, tile4 + (z & (RING - 1)) * plane4, 2 * ox, oy, oz + z, t);
+        tma_store_commit_and_wait_read();   // the slots are cleared next: the TMA unit must have read them
+      }
+      __syncwarp();
+    } else {
+      const int TXH = TX / 2;
+      for (int z = z0; z < z1; ++z) {
+        const float4* pl = tile4 + (z & (RING - 1)) * plane4;
+        const int gz = mod_idx(oz + z, g.nf[2]);
+        for (int i = lane; i < plane4; i += 32) {
+          const float4 v = pl[i];
+          if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+          const int gx = mod_idx(ox + 2 * (i % TXH), g.nf[0]);
+          const int gy = mod_idx(oy + i / TXH, g.nf[1]);
+          red_add(reinterpret_cast<float4*>(fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx), v);
+        }
+      }
+      __syncwarp();
+    }
+    for (int z = z0; z < z1; ++z) {
+      float4* pl = tile4 + (z & (RING - 1)) * plane4;
+      for (int i = lane; i < plane4; i += 32) pl[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+  };
+
+  // Slot sl holds the tile cell pair P in [wx, wx + 4) with (P & 3) == sl.
+  auto pair_of = [](int wx, int sl) { return wx + ((sl - wx) & 3); };
+  auto store_all = [&]() {
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      const int P = pair_of(cur_wx, sl);
+      if (ok0) row0[P] = acc[sl][0];
+      if (ok1) row1[P] = acc[sl][1];
+    }
+  };
+  auto load_all = [&]() {
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      const int P = pair_of(cur_wx, sl);
+      if (ok0) acc[sl][0] = row0[P];
+      if (ok1) acc[sl][1] = row1[P];
+    }
+  };
+  // A run with window `win` starts (-1: none). Branch-free on the slot index: every slot computes
+  // which pair it holds and whether that pair leaves the window (predicated 128-bit store + load).
+  auto open_window = [&](int win) {
+    const int nwx = win % kWinStride, nwyz = win / kWinStride;
+    const int nwy = nwyz % kWinStride, nwz = nwyz / kWinStride;
+    if (have && win >= 0 && nwy == cur_wy && nwz == cur_wz) {   // same sweep: the window moved right
+      const int d = nwx - cur_wx;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int P = pair_of(cur_wx, sl);
+        if (P - cur_wx < d) {             // leaves: store it, load the pair of the new window that takes the slot
+          const int Q = pair_of(nwx, sl);
+          if (ok0) { row0[P] = acc[sl][0]; acc[sl][0] = row0[Q]; }
+          if (ok1) { row1[P] = acc[sl][1]; acc[sl][1] = row1[Q]; }
+        }
+      }
+      cur_wx = nwx;
+      return;
+    }
+    if (have) store_all();
+    __syncwarp();   // other lanes owned the new sweep's rows before
+    have = win >= 0;
+    if (!have) return;
+    if (zbase < 0) zbase = 2 * nwz;
+    if (2 * nwz > zbase) {   // deeper window: the planes left behind are complete
+      retire_planes(zbase, min(2 * nwz, zbase + RING));
+      zbase = 2 * nwz;
+    }
+    cur_wx = nwx;
+    cur_wy = nwy;
+    cur_wz = nwz;
+    const int zp = (2 * nwz + 2 * zg) & (RING - 1);   // even, so the lane's two planes are ring slots zp, zp + 1
+    row0 = tile4 + zp * plane4 + 2 * nwy * (TX / 2) + lane_row4;
+    row1 = row0 + plane4;
+    load_all();
+  };
+
+  const int nbatch = (np + BS - 1) / BS;
+  for (int bb = 0; bb < nbatch; ++bb) {
+    stage_write(bb);
+    __syncwarp();
+    if (bb + 1 < nbatch) fetch(bb + 1);
+
+    const int cnt = min(BS, np - bb * BS);
+    struct PRec { float4 xa, xb; float wy; float2 wz; float2 cc; };
+    auto ld = [&](PRec& R, int p) {
+      const float* rec = stage + p * SW;
+      R.xa = *reinterpret_cast<const float4*>(rec);
+      R.xb = *reinterpret_cast<const float4*>(rec + 4);
+      R.wy = rec[Rec::kWy + r];
+      R.wz = *reinterpret_cast<const float2*>(rec + Rec::kWz + 2 * zg);
+      R.cc = *reinterpret_cast<const float2*>(rec + Rec::kC);
+    };
+    auto comp = [&](const PRec& R, int p) {
+      if ((run_mask >> p) & 1u) open_window(__float_as_int(stage[p * SW + Rec::kHdr]) >> 1);   // warp-uniform
+      const float cre = R.cc.x * R.wy, cim = R.cc.y * R.wy;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float wz = k == 0 ? R.wz.x : R.wz.y;
+        const float2 cw = make_float2(cre * wz, cim * wz);
+        fma_cell<PACK>(acc[0][k].x, acc[0][k].y, R.xa.x, cw);
+        fma_cell<PACK>(acc[0][k].z, acc[0][k].w, R.xa.y, cw);
+        fma_cell<PACK>(acc[1][k].x, acc[1][k].y, R.xa.z, cw);
+        fma_cell<PACK>(acc[1][k].z, acc[1][k].w, R.xa.w, cw);
+        fma_cell<PACK>(acc[2][k].x, acc[2][k].y, R.xb.x, cw);
+        fma_cell<PACK>(acc[2][k].z, acc[2][k].w, R.xb.y, cw);
+        fma_cell<PACK>(acc[3][k].x, acc[3][k].y, R.xb.z, cw);
+        fma_cell<PACK>(acc[3][k].z, acc[3][k].w, R.xb.w, cw);
+      }
+    };
+    PRec A, B, C;
+    ld(A, 0);
+    ld(B, 1);
+    ld(C, 2);
+    int p = 0;
+    for (; p + 3 <= cnt; p += 3) {
+      comp(A, p);
+      ld(A, p + 3);
+      comp(B, p + 1);
+      ld(B, p + 4);
+      comp(C, p + 2);
+      ld(C, p + 5);
+    }
+    if (p < cnt) {
+      comp(A, p);
+      if (p + 1 < cnt) comp(B, p + 1);
+    }
+    __syncwarp();
+  }
+  open_window(-1);   // stores the last window
+  if (zbase >= 0) retire_planes(zbase, min(zbase + RING, TZ));
 }
 
 }  // namespace b200
