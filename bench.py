@@ -375,7 +375,7 @@ def run_ours(args, rank_id, world, device):
     # ---- type-2 block: cfg4 as north_star shards it (2 coils per GPU) ----
     c4 = CONFIGS["cfg4"]
     r4 = device_arm("cfg4", c4, c4["coils"], dist, device, args.steps, args.warmup, 2000 + rank_id)
-    ms4, h2d4, d2h4 = e2e_arm(c4, c4["coils"], dist, max(2, args.steps // 2), 1, 2000 + rank_id)
+    ms4, h2d4, d2h4 = e2e_arm(c4, c4["coils"], dist, max(2, args.steps // 2), 3, 2000 + rank_id)
     u4 = world * c4["coils"] * r4["M"]
     line["type2"] = {
         "workload": f"cfg4: {c4['desc']}", "value": u4 / (r4["ms_per_step"] * 1e-3), "unit": "points/s",

@@ -100,3 +100,36 @@ def binsort_np(folded, fine_dims, bin_dims, rounding=0):
   sizes = np.bincount(key, minlength=nbtot).astype(np.int32)
   start = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
   return idx, start, sizes
+
+
+def nudft_samples(src, pts_tf, grid, ttype, sign, n_samples=256, seed=0):
+  """Float64 direct NUDFT of a random SAMPLE of the outputs (cheap at any size): returns
+  (flat output indices, truth[T][n_samples]). src: [T, M] (type 1) or [T, *grid] (type 2);
+  pts_tf: [M, rank] in the op's layout; grid in TF order; output flattened in TF (row-major) order."""
+  rng = np.random.default_rng(seed)
+  pts = np.asarray(pts_tf, np.float64)
+  M, rank = pts.shape
+  T = src.shape[0]
+  ks = [np.arange(n, dtype=np.float64) - (n // 2) for n in grid]
+  src = np.asarray(src, np.complex128)
+  if ttype == 2:
+    sel = rng.choice(M, size=min(n_samples, M), replace=False)
+    f = src.reshape((T,) + tuple(grid))
+    out = np.empty((T, sel.size), np.complex128)
+    for i, j in enumerate(sel):
+      ph = [np.exp(1j * sign * pts[j, d] * ks[d]) for d in range(rank)]
+      v = f
+      for d in range(rank - 1, -1, -1):   # contract the last axis each time
+        v = v @ ph[d]
+      out[:, i] = v
+    return sel, out
+  N = int(np.prod(grid))
+  sel = rng.choice(N, size=min(n_samples, N), replace=False)
+  kidx = np.unravel_index(sel, grid)
+  out = np.empty((T, sel.size), np.complex128)
+  for i in range(sel.size):
+    ph = np.zeros(M)
+    for d in range(rank):
+      ph += pts[:, d] * ks[d][kidx[d][i]]
+    out[:, i] = src.reshape(T, M) @ np.exp(1j * sign * ph)
+  return sel, out

@@ -264,7 +264,20 @@ def test_low_upsampling_mode_matches_reference_direct(case):
     want = rp.execute(src.reshape(T, -1))
     rp.close()
     err = H.rel_l2(out.reshape(T, -1), want)
-    assert err <= gate, f"sigma 1.25 {case} type {tt}: rel L2 {err:.3e} (ns {rp.kernel_width}, nf {rp.fine_dims})"
+    if cd == np.complex128:
+      assert err <= gate, f"sigma 1.25 {case} type {tt}: rel L2 {err:.3e} (ns {rp.kernel_width}, nf {rp.fine_dims})"
+      continue
+    # complex64 at sigma = 1.25 is ill-conditioned in ANY implementation: the deconvolution divides by
+    # kernel transforms ~1e-5 of their peak at the band edge, which turns the float32 rounding of the
+    # fine grid (summation order!) into ~1e-5 ... 1e-4 of the result -- the reference's own float
+    # result is that far from the truth. So: both against a float64 NUDFT of sampled outputs; the
+    # engine must be at least as accurate as the reference plan, and the two must agree to within
+    # a few times that common error level.
+    sel, truth = H.nudft_samples(src.reshape(T, -1) if tt == 1 else src, pts, grid, tt, sign, 200, 7)
+    e_ours = H.rel_l2(out.reshape(T, -1)[:, sel], truth)
+    e_ref = H.rel_l2(want[:, sel], truth)
+    assert e_ours <= max(1.25 * e_ref, gate), f"sigma 1.25 {case} type {tt}: ours {e_ours:.3e} vs reference {e_ref:.3e} (truth: float64 NUDFT)"
+    assert err <= max(4 * e_ref, gate), f"sigma 1.25 {case} type {tt}: rel L2 vs reference {err:.3e}, reference vs truth {e_ref:.3e}"
 
 
 def test_automatic_upsampling_follows_the_reference_rule():
