@@ -573,12 +573,13 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
 template <typename F>
 cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* fw, Cplx<F>* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
-  const int use_tma = (p->opts.reserved[0] == 0 && ensure_tile_map(p, &p->tmap_in, fw, ntr, p->rl.TX, p->rl.TY, 1)) ? 1 : 0;
+  const int use_tma = (p->rank == 2 && p->opts.reserved[0] == 0 &&
+                       ensure_tile_map(p, &p->tmap_in, fw, ntr, p->rl.TX, p->rl.TY, 1)) ? 1 : 0;
   dim3 grid(static_cast<unsigned>(p->sub_bound), ntr);
   const size_t smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
 #define RL_CASE(PXT, LP)                                                                         \
   if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
-    auto k = interp_rowlane_kernel<F, PXT, LP, 4>;                                               \
+    auto k = p->rank == 3 ? interp_rowlane_kernel<F, PXT, LP, 4, 3> : interp_rowlane_kernel<F, PXT, LP, 4, 2>; \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 128, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,   \
@@ -597,7 +598,7 @@ cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* c, 
   const size_t smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
 #define RL_CASE(PXT, LP)                                                                         \
   if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
-    auto k = spread_rowlane_kernel<F, PXT, LP>;                                                  \
+    auto k = p->rank == 3 ? spread_rowlane_kernel<F, PXT, LP, 3> : spread_rowlane_kernel<F, PXT, LP, 2>; \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<grid, 32, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,    \
@@ -1091,9 +1092,10 @@ int create_impl(b200nufft_plan* p) {
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
   p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
-  // 2D complex128, and 2D complex64 with widths the float tile kernels do not cover (ns 8..15):
-  // row-lane tile kernels (rowlane.cuh) unless the generic kernels are asked for
-  const bool rl_ok = p->rank == 2 && ns <= 15 && (p->is_double || ns > 7);
+  // complex128, and complex64 with widths the float tile kernels do not cover (ns 8..15; e.g.
+  // sigma = 1.25 at tol 1e-6 -> ns = 10), 2D and 3D: row-lane tile kernels (rowlane.cuh) unless the
+  // generic kernels are asked for
+  const bool rl_ok = p->rank >= 2 && ns <= 15 && (p->is_double || ns > 7);
   if (rl_ok) {
     if (p->opts.spread_method != 1) p->spread_method = 5;
     if (p->opts.interp_method != 1) p->interp_method = 5;
@@ -1125,6 +1127,7 @@ int create_impl(b200nufft_plan* p) {
     if (p->type == 2 && p->interp_method == 3) def_bin[1] = 8;   // cfg3-type2 1.18 vs 1.35 ms at 16 x 16 x 2
     if (p->type == 1 && p->spread_method == 2) def_bin[1] = 8;   // cfg3 2.79 vs 3.01 ms at 16 x 16 x 2 (TMA flush)
     if (p->type == 1 && p->spread_method == 7) { def_bin[1] = 8; def_bin[2] = 16; }   // ring of 8 planes: depth is free
+    if (rl_ok) { def_bin[0] = p->is_double ? 8 : 16; def_bin[1] = 8; def_bin[2] = 4; }   // tile = bin + ns + 1 per dim
   }
   p->nbtot = 1;
   for (int d = 0; d < 3; ++d) {
@@ -1157,7 +1160,7 @@ int create_impl(b200nufft_plan* p) {
   }
   const bool uses_tile_i = (p->type == 2 || p->opts.spread_only) ? p->interp_method >= 2 : false;
   if (rl_ok && (p->spread_method == 5 || p->interp_method == 5)) {
-    p->rl = rowlane_geom(p->bin, ns, p->rl_pxt, p->rl_lp, p->R, p->PX, p->PY, p->is_double ? 0 : 1);
+    p->rl = rowlane_geom(p->bin, p->rank, ns, p->rl_pxt, p->rl_lp, p->R, p->PX, p->PY, p->is_double ? 0 : 1);
     p->tile_smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
     if (p->tile_smem > 227 * 1024) {   // user-chosen bins too large: fall back to the generic kernels
       p->spread_method = 1;

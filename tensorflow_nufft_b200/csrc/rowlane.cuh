@@ -1,5 +1,7 @@
-// rowlane.cuh -- shared-memory tile kernels in 2D for the cases the float tile kernels do not
-// cover: complex128 (any kernel width <= 15) and complex64 with widths 8..15 (tol < 1e-6).
+// rowlane.cuh -- shared-memory tile kernels in 2D and 3D for the cases the float tile kernels do
+// not cover: complex128 (any kernel width <= 15) and complex64 with widths 8..15 (tol < 1e-6, or
+// the low-upsampling mode sigma = 1.25). In 3D a lane walks its row through the ns z-planes of the
+// stencil (the tile is bin + halo in all three dimensions, staged with wrapped asynchronous copies).
 //
 // Same sums as spread.cuh / interp.cuh (reference: SpreadSubproblem2DKernel / InterpSubproblem2DKernel
 // nufft_plan.cu.cc:790-878, 1041-1110) (tol 1e-12 -> ns = 14: 196 cells of 16 bytes per point).
@@ -24,32 +26,36 @@
 namespace b200 {
 
 struct RowLaneGeom {
-  int TX, TY;     // tile extent in cells (TX odd)
-  int hx, hy;     // tile origin = bin origin - (hx, hy)
-  int R, PX, PY;  // record stride, wy offset and wy length, in reals (rows >= PY carry no weight)
+  int TX, TY, TZ; // tile extent in cells (TX odd; TZ = 1 in 2D)
+  int hx, hy, hz; // tile origin = bin origin - (hx, hy, hz)
+  int R, PX, PY;  // record stride, wy offset and wy / wz length, in reals (rows >= PY carry no weight)
+  int ns;         // kernel width (z taps walked in 3D)
 };
 
 // align_x: the records' x start is moved down to an even cell (complex64): one more halo cell.
-inline RowLaneGeom rowlane_geom(const int* bin, int ns, int pxt, int lp, int R, int PX, int PY, int align_x) {
+inline RowLaneGeom rowlane_geom(const int* bin, int rank, int ns, int pxt, int lp, int R, int PX, int PY, int align_x) {
   RowLaneGeom r;
   r.hx = (ns + 1) / 2 + (align_x ? 1 : 0);
   r.hy = (ns + 1) / 2;
+  r.hz = rank > 2 ? (ns + 1) / 2 : 0;
   r.TX = (bin[0] + pxt + 2 + (align_x ? 2 : 0)) | 1;
   r.TY = bin[1] + lp + 2;
+  r.TZ = rank > 2 ? bin[2] + ns + 1 : 1;
   r.R = R;
   r.PX = PX;
   r.PY = PY;
+  r.ns = ns;
   return r;
 }
 
 inline size_t rowlane_smem_bytes(const RowLaneGeom& r, size_t cell_bytes) {
-  return ((static_cast<size_t>(r.TX) * r.TY * cell_bytes + 127) & ~static_cast<size_t>(127)) + 16;
+  return ((static_cast<size_t>(r.TX) * r.TY * r.TZ * cell_bytes + 127) & ~static_cast<size_t>(127)) + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
 // type 2
 // ------------------------------------------------------------------------------------------------
-template <typename F, int PXT, int LP, int WARPS>
+template <typename F, int PXT, int LP, int WARPS, int RANK>
 __global__ void __launch_bounds__(WARPS * 32)
 interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
@@ -68,16 +74,20 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
   const int b = sd.x, p0 = sd.y, np = sd.z;
-  const int TX = rl.TX, TY = rl.TY;
+  const int TX = rl.TX, TY = rl.TY, TZ = RANK > 2 ? rl.TZ : 1;
   const int bx = b % g.nbins[0];
-  const int by = b / g.nbins[0];
-  const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy;
-  const int ncell = TX * TY;
+  const int by = (b / g.nbins[0]) % g.nbins[1];
+  const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
+  const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy, oz = RANK > 2 ? bz * g.bin[2] - rl.hz : 0;
+  const int plane = TX * TY;
+  const int ncell = plane * TZ;
   uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(tile_rl) + ((static_cast<size_t>(ncell) * sizeof(C) + 127) & ~static_cast<size_t>(127)));
   const C* fwt = fw + static_cast<int64_t>(t) * g.nftot;
   C* ct = c + static_cast<int64_t>(t) * M;
 
-  const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1];
+  // 2D interior tiles: one TMA box. 3D (and tiles that straddle the periodic boundary): per-cell
+  // asynchronous copies with index wrap (the odd tile pitch rules out 128-byte aligned plane boxes).
+  const bool interior = RANK == 2 && use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1];
   if (interior) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -89,10 +99,12 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   } else {
     for (int i = tid; i < ncell; i += WARPS * 32) {
       const int ix = i % TX;
-      const int iy = i / TX;
+      const int iy = (i / TX) % TY;
+      const int iz = i / plane;
       const int gx = mod_idx(ox + ix, g.nf[0]);
       const int gy = mod_idx(oy + iy, g.nf[1]);
-      __pipeline_memcpy_async(&tile_rl[i], fwt + static_cast<int64_t>(gy) * g.nf[0] + gx, sizeof(C));
+      const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
+      __pipeline_memcpy_async(&tile_rl[i], fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx, sizeof(C));
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -103,6 +115,7 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const int pt = lane / LP;
   const int row = lane % LP;
   const int ngrp = (np + PW - 1) / PW;
+  const int nz = RANK > 2 ? rl.ns : 1;
   for (int grp = warp; grp < ngrp; grp += WARPS) {
     const int p = grp * PW + pt;
     const bool valid = p < np;
@@ -112,19 +125,29 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
       const int64_t j = static_cast<int64_t>(p0) + p;
       const int4 st = start[j];
       id = idx[j];
-      const int rx = st.x - ox, ry = st.y - oy;
+      const int rx = st.x - ox, ry = st.y - oy, rz = RANK > 2 ? st.z - oz : 0;
       // Memory safety for coordinates outside the declared points_range (see interp.cuh).
-      const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY;
+      const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY && (RANK < 3 || (rz >= 0 && rz + nz <= TZ));
       if (fits) {
         const F* wx = wrec + j * rl.R;
         const F wy = row < rl.PY ? wx[rl.PX + row] : F(0);
-        const C* ptr = tile_rl + (ry + row) * TX + rx;
+        const F* wz = wx + rl.PX + rl.PY;
+        const C* ptr = tile_rl + (rz * TY + ry + row) * TX + rx;
+        C w2[PXT / 2];
 #pragma unroll
-        for (int k = 0; k < PXT; k += 2) {
-          const C w2 = *reinterpret_cast<const C*>(wx + k);   // two consecutive weights
-          const C v0 = ptr[k], v1 = ptr[k + 1];
-          re += v0.x * w2.x + v1.x * w2.y;
-          im += v0.y * w2.x + v1.y * w2.y;
+        for (int k = 0; k < PXT; k += 2) w2[k / 2] = *reinterpret_cast<const C*>(wx + k);   // two consecutive weights
+        for (int dz = 0; dz < nz; ++dz) {
+          F pr = F(0), pi = F(0);
+#pragma unroll
+          for (int k = 0; k < PXT; k += 2) {
+            const C v0 = ptr[k], v1 = ptr[k + 1];
+            pr += v0.x * w2[k / 2].x + v1.x * w2[k / 2].y;
+            pi += v0.y * w2[k / 2].x + v1.y * w2[k / 2].y;
+          }
+          const F wzd = RANK > 2 ? wz[dz] : F(1);
+          re += wzd * pr;
+          im += wzd * pi;
+          ptr += plane;
         }
         re *= wy;
         im *= wy;
@@ -143,7 +166,7 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
 // type 1: one-warp CTAs, private tile, one point per step. lane = half * 16 + row (LP <= 16):
 // a quarter warp = 8 consecutive rows of the same half-row, conflict-free with the odd pitch.
 // ------------------------------------------------------------------------------------------------
-template <typename F, int PXT, int LP>
+template <typename F, int PXT, int LP, int RANK>
 __global__ void __launch_bounds__(32)
 spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
@@ -161,11 +184,13 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const int lane = threadIdx.x;
   const int t = blockIdx.y;
   const int b = sd.x, p0 = sd.y, np = sd.z;
-  const int TX = rl.TX, TY = rl.TY;
+  const int TX = rl.TX, TY = rl.TY, TZ = RANK > 2 ? rl.TZ : 1;
   const int bx = b % g.nbins[0];
-  const int by = b / g.nbins[0];
-  const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy;
-  const int ncell = TX * TY;
+  const int by = (b / g.nbins[0]) % g.nbins[1];
+  const int bz = RANK > 2 ? b / (g.nbins[0] * g.nbins[1]) : 0;
+  const int ox = bx * g.bin[0] - rl.hx, oy = by * g.bin[1] - rl.hy, oz = RANK > 2 ? bz * g.bin[2] - rl.hz : 0;
+  const int plane = TX * TY;
+  const int ncell = plane * TZ;
   const C* ct = c + static_cast<int64_t>(t) * M;
   C* fwt = fw + static_cast<int64_t>(t) * g.nftot;
 
@@ -176,12 +201,14 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const int half = lane >> 4;
   const int row = lane & 15;
   const bool row_ok = row < LP;
+  const int nz = RANK > 2 ? rl.ns : 1;
 
   // one-point software pipeline: the record of point p + 1 is fetched while point p is applied
   F wxh[HW];
   F wy = F(0);
   int4 st = make_int4(0, 0, 0, 0);
   C cj = make_cplx<F>(F(0), F(0));
+  const F* wz_n = wrec;
   auto fetch = [&](int p) {
     if (p < np) {
       const int64_t j = static_cast<int64_t>(p0) + p;
@@ -193,6 +220,7 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
         wxh[k + 1] = w2.y;
       }
       wy = (row_ok && row < rl.PY) ? wx[rl.PX + row] : F(0);
+      wz_n = wx + rl.PX + rl.PY;
       st = start[j];
       cj = ct[idx[j]];
     }
@@ -203,21 +231,27 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
 #pragma unroll
     for (int k = 0; k < HW; ++k) w[k] = wxh[k];
     const F cr = cj.x * wy, ci = cj.y * wy;
-    const int rx = st.x - ox, ry = st.y - oy;
+    const int rx = st.x - ox, ry = st.y - oy, rz = RANK > 2 ? st.z - oz : 0;
+    const F* wz = wz_n;
     fetch(p + 1);
     // Memory safety for coordinates outside the declared points_range: such a window does not lie
     // in this bin's tile and the point is dropped (the reference's behaviour is undefined there).
-    const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY;
+    const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY && (RANK < 3 || (rz >= 0 && rz + nz <= TZ));
     if (fits && row_ok) {
-      C* ptr = tile_rl + (ry + row) * TX + rx + half * HW;
-      C v[HW];
+      C* ptr = tile_rl + (rz * TY + ry + row) * TX + rx + half * HW;
+      for (int dz = 0; dz < nz; ++dz) {
+        const F wzd = RANK > 2 ? wz[dz] : F(1);
+        const F czr = cr * wzd, czi = ci * wzd;
+        C v[HW];
 #pragma unroll
-      for (int k = 0; k < HW; ++k) v[k] = ptr[k];
+        for (int k = 0; k < HW; ++k) v[k] = ptr[k];
 #pragma unroll
-      for (int k = 0; k < HW; ++k) {
-        v[k].x += cr * w[k];
-        v[k].y += ci * w[k];
-        ptr[k] = v[k];
+        for (int k = 0; k < HW; ++k) {
+          v[k].x += czr * w[k];
+          v[k].y += czi * w[k];
+          ptr[k] = v[k];
+        }
+        ptr += plane;
       }
     }
     __syncwarp();
@@ -228,10 +262,12 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
     const C v = tile_rl[i];
     if (v.x == F(0) && v.y == F(0)) continue;
     const int ix = i % TX;
-    const int iy = i / TX;
+    const int iy = (i / TX) % TY;
+    const int iz = i / plane;
     const int gx = mod_idx(ox + ix, g.nf[0]);
     const int gy = mod_idx(oy + iy, g.nf[1]);
-    red_add(fwt + static_cast<int64_t>(gy) * g.nf[0] + gx, v);
+    const int gz = RANK > 2 ? mod_idx(oz + iz, g.nf[2]) : 0;
+    red_add(fwt + (static_cast<int64_t>(gz) * g.nf[1] + gy) * g.nf[0] + gx, v);
   }
 }
 
