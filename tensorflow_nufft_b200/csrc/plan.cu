@@ -591,6 +591,8 @@ cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* fw,
   return cudaErrorInvalidValue;
 }
 
+constexpr int kRowLaneWarps3D = 4;   // warps sharing one 3D row-lane spreader tile (z-plane ownership)
+
 template <typename F>
 cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* c, Cplx<F>* fw, cudaStream_t st) {
   GridGeom g = grid_geom(p);
@@ -598,10 +600,10 @@ cudaError_t launch_spread_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* c, 
   const size_t smem = rowlane_smem_bytes(p->rl, sizeof(Cplx<F>));
 #define RL_CASE(PXT, LP)                                                                         \
   if (p->rl_pxt == PXT && p->rl_lp == LP) {                                                      \
-    auto k = p->rank == 3 ? spread_rowlane_kernel<F, PXT, LP, 3> : spread_rowlane_kernel<F, PXT, LP, 2>; \
+    auto k = p->rank == 3 ? spread_rowlane_kernel<F, PXT, LP, 3, kRowLaneWarps3D> : spread_rowlane_kernel<F, PXT, LP, 2, 1>; \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    k<<<grid, 32, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,    \
+    k<<<grid, p->rank == 3 ? 32 * kRowLaneWarps3D : 32, smem, st>>>(p->M, g, p->rl, p->sub_total(), p->sub_desc.as<int4>(), p->idx,    \
                               p->start.as<int4>(), p->wrec.as<F>(), c, fw);                      \
     return cudaGetLastError();                                                                   \
   }

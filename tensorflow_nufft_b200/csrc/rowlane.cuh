@@ -166,8 +166,12 @@ interp_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
 // type 1: one-warp CTAs, private tile, one point per step. lane = half * 16 + row (LP <= 16):
 // a quarter warp = 8 consecutive rows of the same half-row, conflict-free with the odd pitch.
 // ------------------------------------------------------------------------------------------------
-template <typename F, int PXT, int LP, int RANK>
-__global__ void __launch_bounds__(32)
+// 3D: WPT warps share the tile with exclusive ownership of its z-planes (plane z belongs to warp
+// z % WPT): every warp walks all points of the subproblem and updates only the stencil planes it
+// owns, so there are still no atomics and WPT warps hide each other's latency (the tile of a wide
+// kernel fills most of the SM's shared memory: one CTA per SM).
+template <typename F, int PXT, int LP, int RANK, int WPT>
+__global__ void __launch_bounds__(32 * WPT)
 spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restrict__ sub_total,
                       const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                       const int4* __restrict__ start, const F* __restrict__ wrec,
@@ -181,7 +185,8 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const int nsub_live = *sub_total;
   const int4 sd = sub_desc[s];
   if (s >= nsub_live) return;
-  const int lane = threadIdx.x;
+  static_assert(WPT == 1 || RANK == 3, "plane ownership is 3D only");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
   const int b = sd.x, p0 = sd.y, np = sd.z;
   const int TX = rl.TX, TY = rl.TY, TZ = RANK > 2 ? rl.TZ : 1;
@@ -194,8 +199,8 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
   const C* ct = c + static_cast<int64_t>(t) * M;
   C* fwt = fw + static_cast<int64_t>(t) * g.nftot;
 
-  for (int i = lane; i < ncell; i += 32) tile_rl[i] = make_cplx<F>(F(0), F(0));
-  __syncwarp();
+  for (int i = tid; i < ncell; i += 32 * WPT) tile_rl[i] = make_cplx<F>(F(0), F(0));
+  if (WPT > 1) __syncthreads(); else __syncwarp();
 
   constexpr int HW = PXT / 2;          // cells per half row
   const int half = lane >> 4;
@@ -238,8 +243,10 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
     // in this bin's tile and the point is dropped (the reference's behaviour is undefined there).
     const bool fits = rx >= 0 && rx + PXT <= TX && ry >= 0 && ry + LP <= TY && (RANK < 3 || (rz >= 0 && rz + nz <= TZ));
     if (fits && row_ok) {
-      C* ptr = tile_rl + (rz * TY + ry + row) * TX + rx + half * HW;
-      for (int dz = 0; dz < nz; ++dz) {
+      // first stencil plane owned by this warp: (rz + dz) % WPT == warp
+      const int dz0 = WPT > 1 ? (((warp - rz) % WPT) + WPT) % WPT : 0;
+      C* ptr = tile_rl + ((rz + dz0) * TY + ry + row) * TX + rx + half * HW;
+      for (int dz = dz0; dz < nz; dz += WPT) {
         const F wzd = RANK > 2 ? wz[dz] : F(1);
         const F czr = cr * wzd, czi = ci * wzd;
         C v[HW];
@@ -251,14 +258,15 @@ spread_rowlane_kernel(int64_t M, GridGeom g, RowLaneGeom rl, const int* __restri
           v[k].y += czi * w[k];
           ptr[k] = v[k];
         }
-        ptr += plane;
+        ptr += WPT * plane;
       }
     }
     __syncwarp();
   }
+  if (WPT > 1) __syncthreads();
 
   // flush: native global reductions (REDG.F64 / REDG.F32x2), periodic wrap, untouched cells skipped
-  for (int i = lane; i < ncell; i += 32) {
+  for (int i = tid; i < ncell; i += 32 * WPT) {
     const C v = tile_rl[i];
     if (v.x == F(0) && v.y == F(0)) continue;
     const int ix = i % TX;
