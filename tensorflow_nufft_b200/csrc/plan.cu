@@ -406,7 +406,9 @@ cudaError_t launch_spread_sweep2d(const b200nufft_plan* p, int ntr, const float2
   const int64_t nblocks = p->sub_bound * ngroups;
   if (nblocks > 2147483647LL) return cudaErrorInvalidValue;
   const size_t smem = spread_sweep2d_smem_bytes<Y>(p->bin);
-  const int use_tma = (p->opts.reserved[5] == 0 &&
+  // TMA tile flush needs 128-byte aligned coil tiles in shared memory
+  const bool tile_ok = ((p->bin[0] + kSweepHaloX) * (p->bin[1] + 8) * sizeof(float2)) % 128 == 0;
+  const int use_tma = (p->opts.reserved[5] == 0 && tile_ok &&
                        ensure_out_tensor_map(const_cast<b200nufft_plan*>(p), fw, ntr, 0, kSweepHaloX)) ? 1 : 0;
   const bool pack = p->opts.reserved[3] == 0;
 #define SWEEP_CASE(NS)                                                                            \
