@@ -914,13 +914,18 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.rounding = 0;
   for (int d = 0; d < 3; ++d) { bg.nf[d] = p->nf[d]; bg.bin[d] = p->bin[d]; bg.nbins[d] = p->nbins[d]; }
   bg.ws = p->ws ? 1 : 0;
-  bg.WX = p->bin[0] / 2 + 3;
-  bg.WY = p->ws2 ? p->bin[1] / 2 + 3 : p->bin[1] + 7;
+  // Window counts per bin and dimension. Even-aligned stencil starts (relative to the tile origin
+  // bin - 4) run from 0 to bin + 4 - ns/2, i.e. (bin + 4 - ns/2) / 2 + 1 window positions; unaligned
+  // ones (first-generation window sort) use every row.
+  const int wmax_x = (p->bin[0] + 4 - p->kp.ns / 2) / 2 + 1;
+  const int wmax_y = (p->bin[1] + 4 - p->kp.ns / 2) / 2 + 1;
+  const int wmax_z = (p->bin[2] + 4 - p->kp.ns / 2) / 2 + 1;
+  bg.WX = (p->ws2 || p->ws3) ? wmax_x : p->bin[0] / 2 + 3;
+  bg.WY = (p->ws2 || p->ws3) ? wmax_y : p->bin[1] + 7;
   bg.align_x = p->is_double ? 0 : 1;
   bg.align_y = (p->ws2 || p->ws3) ? 1 : 0;
-  if (p->ws3) bg.WY = p->bin[1] / 2 + 3;
   bg.align_z = p->ws3 ? 1 : 0;
-  bg.WZ = p->ws3 ? p->bin[2] / 2 + 3 : 1;
+  bg.WZ = p->ws3 ? wmax_z : 1;
   const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY * bg.WZ : 1);
 
   if (skip) {

@@ -176,7 +176,7 @@ constexpr int kSortThreads = kSortWarps * 32;
 constexpr int kSortRounds = 8;
 constexpr int kSortPerWarp = 32 * kSortRounds;             // 256
 constexpr int kSortTile = kSortWarps * kSortPerWarp;       // 2048
-constexpr int kRadixBitsMax = 10;                          // 8-bit digits, or 10-bit when that saves a pass
+constexpr int kRadixBitsMax = 11;                          // 8-bit digits, or 10 / 11-bit when that saves a pass
 
 template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
@@ -205,7 +205,9 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
                      const int* __restrict__ skip) {
   if (skip != nullptr && *skip) return;
   constexpr int RADIX = 1 << BITS;
-  __shared__ int cnt[kSortWarps][RADIX];   // running per-warp digit counts
+  // running per-warp digit counts; a tile holds 2048 elements, so 16 bits are enough (and keep the
+  // 11-bit variant inside the 48 KB of static shared memory)
+  __shared__ unsigned short cnt[kSortWarps][RADIX];
   __shared__ int gbase[RADIX];             // global base of each digit for this block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kSortWarps * RADIX; i += kSortThreads) (&cnt[0][0])[i] = 0;
@@ -229,7 +231,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
     int prev = 0;
     if (ok) prev = cnt[warp][dig];
     __syncwarp();
-    if (ok && before == 0) cnt[warp][dig] = prev + __popc(peers);
+    if (ok && before == 0) cnt[warp][dig] = static_cast<unsigned short>(prev + __popc(peers));
     __syncwarp();
     rank[r] = prev + before;
   }
@@ -240,7 +242,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       int c = cnt[w][d];
-      cnt[w][d] = run;
+      cnt[w][d] = static_cast<unsigned short>(run);
       run += c;
     }
   }
@@ -267,17 +269,24 @@ inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_
   uint32_t* kin = k0; int* vin = v0; uint32_t* kout = k1; int* vout = v1;
   if (n > 0) {
     const int nblk = static_cast<int>((n + kSortTile - 1) / kSortTile);
-    // 8-bit digits unless 10-bit digits save a whole pass (cfg2: 20 key bits -> 2 passes, not 3)
-    const int passes8 = key_bits <= 0 ? 0 : (key_bits + 7) / 8;
-    const int passes10 = key_bits <= 0 ? 0 : (key_bits + 9) / 10;
-    const int bits = passes10 < passes8 ? 10 : 8;
-    const int passes = bits == 10 ? passes10 : passes8;
+    // 8-bit digits unless 10-bit digits save a whole pass (cfg2: 20 key bits -> 2 passes of 10).
+    // 11-bit digits (instantiated, off): cfg3's 22-bit window keys in 2 passes instead of 3 were
+    // measured SLOWER (set_points 1.26 vs 1.16 ms): the 2048-entry per-block tables and the 8x larger
+    // histogram scan cost more than the pass they save.
+    int bits = 8;
+    int passes = key_bits <= 0 ? 0 : (key_bits + 7) / 8;
+    for (int b2 : {10}) {
+      const int pb = key_bits <= 0 ? 0 : (key_bits + b2 - 1) / b2;
+      if (pb < passes) { passes = pb; bits = b2; }
+    }
     for (int p = 0; p < passes; ++p) {
       const int shift = p * bits;
-      if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
+      if (bits == 11) radix_hist_kernel<11><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
+      else if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
       else radix_hist_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
       launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << bits) * nblk, scan_tmp, nullptr, stream, skip);
-      if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
+      if (bits == 11) radix_scatter_kernel<11><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
+      else if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
       else radix_scatter_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
       launches += 1;
       std::swap(kin, kout);
