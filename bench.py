@@ -226,8 +226,46 @@ def device_arm(name, cfg, T, dist, device, steps, warmup, seed, want_out=False):
     for k in stage:
       stage[k] += tm[k] / steps
   info = plan.info()
+  # the same step replayed from a CUDA graph (no per-launch CPU cost; matters for launch-bound sizes)
+  graph_ms = None
+  try:
+    gplan = _lib.Plan(ttype, tuple(reversed(grid)), sign, T, float(np.float32(TOL)), _lib.COMPLEX64, device=device,
+                      num_threads_compat=ncores)
+    gplan.reserve(M)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+
+    def gstep(st):
+      for s_ in range(sets):
+        gplan.set_points_interleaved(M, d_pts[s_].data_ptr(), st)
+        if ttype == 1:
+          gplan.execute(d_src[s_].data_ptr(), d_out[s_].data_ptr(), st)
+        else:
+          gplan.execute(d_out[s_].data_ptr(), d_src[s_].data_ptr(), st)
+
+    with torch.cuda.stream(side):
+      gstep(side.cuda_stream)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+      gstep(side.cuda_stream)
+    for _ in range(3):
+      graph.replay()
+    dist.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+      graph.replay()
+    g1.record()
+    dist.barrier()
+    (graph_ms,) = dist.max(g0.elapsed_time(g1) / steps)
+    del graph
+    gplan.close()
+  except Exception as exc:  # pylint: disable=broad-except
+    graph_ms = f"unavailable: {exc}"
   (ms_total,) = dist.max(ms_total)
   res = dict(M=M, rank=rank, T=T, sets=sets, grid=grid, ttype=ttype, ms_per_step=ms_total / steps, stage=stage,
+             graph_ms_per_step=graph_ms,
              launches=int(launches), allocs_in_timed_region=int(allocs), info=info,
              fine=[int(x) for x in info.fine_dims[:rank]], pts_np=pts_np)
   if want_out:
@@ -368,6 +406,7 @@ def run_ours(args, rank_id, world, device):
       "e2e": {"value": units / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
       "gpu_launches": r["launches"],
+      "cuda_graph_ms_per_step": r["graph_ms_per_step"],
       "device_allocations_in_timed_region": r["allocs_in_timed_region"],
       "clocks": clocks,
   }

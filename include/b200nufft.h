@@ -29,6 +29,10 @@
  *   - opts.external_workspace = 1 + b200nufft_workspace_bytes / b200nufft_bind_workspace: the caller
  *     allocates ONE block (allocate_temp / torch.empty) per op call and the plan carves its fine
  *     grid and per-point buffers out of it.
+ * CUDA graphs: after b200nufft_reserve (or with a bound workspace) and with check_points_range = 0,
+ * set_points + execute only enqueue kernels, cuFFT executions and memsets on the caller's stream, so
+ * the pair can be captured into a CUDA graph and replayed (tests/test_gpu_boundary.py; the profile
+ * option records events and is not capturable).
  * Every entry point saves and restores the calling thread's current CUDA device. A handle may be
  * used from several threads / streams: calls on one handle are serialised by a per-plan lock, and
  * work enqueued on a new stream waits (cudaStreamWaitEvent) for the plan's previous work.

@@ -301,11 +301,14 @@ struct PlanCall {
   std::lock_guard<std::mutex> lock;
   DeviceGuard dev;
   cudaStream_t st;
+  bool capturing = false;   // the stream is being captured into a CUDA graph: no cross-stream events
   PlanCall(b200nufft_plan* plan, cudaStream_t stream) : p(plan), lock(plan->mu), dev(plan->device), st(stream) {
-    if (p->has_work && p->done && st != p->last_stream) cudaStreamWaitEvent(st, p->done, 0);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess) capturing = cs != cudaStreamCaptureStatusNone;
+    if (!capturing && p->has_work && p->done && st != p->last_stream) cudaStreamWaitEvent(st, p->done, 0);
   }
   ~PlanCall() {
-    if (p->done && cudaEventRecord(p->done, st) == cudaSuccess) {
+    if (!capturing && p->done && cudaEventRecord(p->done, st) == cudaSuccess) {
       p->has_work = true;
       p->last_stream = st;
     }

@@ -349,7 +349,9 @@ clear_ints_kernel(int* __restrict__ a, int64_t n, const int* __restrict__ skip) 
 // ES kernel value phi(x) = exp(beta * sqrt(1 - c x^2)) for |x| < ns/2, else 0, with the
 // reference CPU evaluator's roundings (evaluate_kernel_vector, nufft_plan.cc:1254-1289):
 // c*x*x in FloatType; 1 - ., sqrt and the product with beta in double; rounded to FloatType;
-// then exp (evaluated in double here and rounded once = correctly rounded FloatType exp).
+// then exp. The shipped build defines B200NUFFT_FAST_EXP (csrc/Makefile): FloatType exp (expf: <= 2 ulp
+// for float; parity with the reference stays at 1.5e-7 ... 3e-7 rel-L2); without the macro the
+// exponential is evaluated in double and rounded once (correctly rounded float exp, ~2x the cost).
 template <typename F>
 __device__ __forceinline__ F es_eval(F x, F beta, F c, F half_width) {
   F t = mul_rn(mul_rn(c, x), x);

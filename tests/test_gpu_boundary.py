@@ -189,3 +189,49 @@ def test_user_batch_size_is_clamped_to_the_grid_limit():
   plan = L.Plan(2, (16, 16), -1, 70000, TOL, L.COMPLEX64, device=0, max_batch_size=70000)
   assert plan.info().batch_size == 65535
   plan.close()
+
+
+@pytest.mark.parametrize("ttype", [1, 2])
+def test_set_points_and_execute_capture_into_a_cuda_graph(ttype):
+  """No allocation, no host synchronisation, no cross-stream events on the hot path: the pair is
+  capturable and the replayed graph gives the same result on new input data."""
+  L = _lib()
+  grid, m, T = (64, 48), 20000, 2
+  N = grid[0] * grid[1]
+  pts = torch.from_numpy(H.uniform_points(m, 2, 61)).cuda()
+  src = torch.from_numpy(H.random_complex((T, m) if ttype == 1 else (T, N), 62)).cuda()
+  out = torch.zeros((T, N) if ttype == 1 else (T, m), dtype=torch.complex64, device="cuda")
+  plan = L.Plan(ttype, grid[::-1], -1, T, TOL, L.COMPLEX64, device=0)
+  plan.reserve(m)
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+
+  def step(stream):
+    plan.set_points_interleaved(m, pts.data_ptr(), stream)
+    if ttype == 1:
+      plan.execute(src.data_ptr(), out.data_ptr(), stream)
+    else:
+      plan.execute(out.data_ptr(), src.data_ptr(), stream)
+
+  with torch.cuda.stream(side):
+    for _ in range(2):
+      step(side.cuda_stream)
+  side.synchronize()
+  want = out.clone()
+  g = torch.cuda.CUDAGraph()
+  a0 = L.alloc_counts()
+  with torch.cuda.graph(g, stream=side):
+    step(side.cuda_stream)
+  assert L.alloc_counts() == a0
+  # new data in the same buffers: replay must transform IT
+  pts.copy_(torch.from_numpy(H.uniform_points(m, 2, 63)).cuda())
+  src.mul_(0.5)
+  torch.cuda.synchronize()
+  g.replay()
+  torch.cuda.synchronize()
+  got = out.clone()
+  step(torch.cuda.current_stream().cuda_stream)   # eager, same inputs
+  torch.cuda.synchronize()
+  assert H.rel_l2(got.cpu().numpy(), out.cpu().numpy()) < 1e-6
+  assert H.rel_l2(got.cpu().numpy(), want.cpu().numpy()) > 0.1
+  plan.close()
