@@ -102,10 +102,14 @@ typedef struct b200nufft_opts {
   int reserved[8];         /* engine A/B switches used by the tests and probes (0 = default):
                               [0] 1: stage interpolator tiles with cp.async instead of TMA
                               [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8, 16)
+                              [2] 1: no pre-clear of the fine grid on the plan's internal stream
                               [3] 1: sweep spreaders use scalar FFMA instead of packed FFMA2
                               [4] 1: single cuFFT 3D plan instead of the pruned three-plan scheme
                               [5] 1: flush spreader tiles with REDG instead of TMA reduce-add
-                              [6] 1: 3D tiles move all their z-planes (no per-subproblem z range) */
+                              [6] 1: 3D tiles move all their z-planes (no per-subproblem z range)
+                              [7] 1: 2D sweep spreader gathers coil-major strengths (no point-major
+                                  pre-pass); 2: 3D sweep spreader of single-transform plans evaluates
+                                  the stencil weights itself (no stencil records; measured slower) */
 } b200nufft_opts;
 
 typedef struct b200nufft_info {

@@ -163,8 +163,8 @@ def make_opts(**opt_kwargs):
   reserved[] A/B switches)."""
   opts = Opts()
   lib().b200nufft_default_opts(ctypes.byref(opts))
-  reserved = {"no_tma": 0, "coils_per_cta": 1, "kernel_variant": 2, "no_pack": 3, "full_fft": 4,
-              "no_tma_flush": 5, "no_zrange": 6, "no_point_major": 7}
+  reserved = {"no_tma": 0, "coils_per_cta": 1, "no_preclear": 2, "no_pack": 3, "full_fft": 4,
+              "no_tma_flush": 5, "no_zrange": 6, "no_point_major": 7, "otf_weights": 7}
   for k, v in opt_kwargs.items():
     if k == "bin_dims":
       for i, b in enumerate(v):

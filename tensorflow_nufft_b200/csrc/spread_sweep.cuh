@@ -26,6 +26,7 @@
 
 #include "dev_common.cuh"
 #include "interp.cuh"
+#include "points.cuh"
 #include "spread.cuh"
 
 namespace b200 {
@@ -409,11 +410,17 @@ inline size_t spread_sweep3d_smem_bytes(const int* bin) {
 // of all bin_z + 8: when wz advances, the planes left behind are complete, leave through the TMA
 // unit (one reduce-add per plane) and are cleared for reuse. 27 KB per one-warp CTA instead of 53,
 // i.e. 7 resident warps per SM instead of 4 (the kernel is latency-bound), whatever the bin depth.
-template <int NS, int PACK>
+// OTF = 1 (opt-in, single-transform plans): the stencil weights are evaluated HERE, in the staging
+// step, from the folded coordinates (same functions as stencil_record8_kernel, so the same bits)
+// instead of being written by set_points (96 + 16 bytes per point) and read back once. Measured on
+// cfg3: set_points 1.18 -> 0.71 ms, but the spreader 1.29 -> 4.85 ms (a lane evaluates its point's
+// 24 kernel values alone: ~1400 serial instructions per batch in a one-warp CTA), so it is OFF.
+template <int NS, int PACK, int OTF>
 __global__ void __launch_bounds__(32)
 spread_sweep3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__ sub_total,
                           const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                           const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][6]*/,
+                          const float4* __restrict__ folded4 /*[M]: x, y, z, 0 (OTF)*/, float es_beta, float es_c, float es_hw,
                           const float2* __restrict__ c, float2* __restrict__ fw,
                           const __grid_constant__ CUtensorMap tmap_out, int use_tma) {
   static_assert(NS <= 7, "8-cell windows");
@@ -455,7 +462,7 @@ spread_sweep3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict_
 
   // ---- register prefetch, two batches deep (see the 2D kernel) ----
   struct Pre {
-    float4 w4[6];
+    float4 w4[OTF ? 1 : 6];   // OTF: w4[0] = folded coordinates (x, y, z, 0)
     int4 st;
     float2 c;
     int id;   // point id of the batch this set fetches NEXT
@@ -465,9 +472,13 @@ spread_sweep3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict_
     const int pl = bb * BS + lane;
     if (pl < np) {
       const int64_t j = p0 + pl;
+      if (OTF) {
+        P.w4[0] = folded4[P.id];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) P.w4[k] = wrec4[j * 6 + k];
-      P.st = start[j];
+        for (int k = 0; k < 6; ++k) P.w4[k] = wrec4[j * 6 + k];
+        P.st = start[j];
+      }
       P.c = ct[P.id];
     }
     const int pl2 = (bb + 2) * BS + lane;
@@ -476,13 +487,35 @@ spread_sweep3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict_
   int last_win = -2;
   unsigned run_mask = 0;
   auto stage_write = [&](Pre& P, int bb) {
-    float4 (&w4)[6] = P.w4;
-    float2& c_n = P.c;
+    float4 w4[6];
+    int4 st_c = P.st;
+    if (OTF) {
+      // stencil start (moved down to an even cell) and the 8 zero-padded, shifted weights per dimension
+      const float xs[3] = {P.w4[0].x, P.w4[0].y, P.w4[0].z};
+      int sts[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int i1 = static_cast<int>(ceilf(sub_rn(xs[d], es_hw)));
+        const float x1 = sub_rn(static_cast<float>(i1), xs[d]);
+        const int shift = i1 & 1;
+        sts[d] = i1 - shift;
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = es_eval_fast<float>(add_rn(x1, static_cast<float>(k - shift)), es_beta, es_c, es_hw);
+        w4[2 * d] = make_float4(w[0], w[1], w[2], w[3]);
+        w4[2 * d + 1] = make_float4(w[4], w[5], w[6], w[7]);
+      }
+      st_c = make_int4(sts[0], sts[1], sts[2], 0);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w4[k] = P.w4[OTF ? 0 : k];
+    }
+    float2 c_n = P.c;
     const int pl = bb * BS + lane;
     float* rec = stage + lane * SW;
     int win = -1;
     if (pl < np) {
-      const int rx = P.st.x - ox, ry = P.st.y - oy, rz = P.st.z - oz;
+      const int rx = st_c.x - ox, ry = st_c.y - oy, rz = st_c.z - oz;
       // Memory safety for coordinates outside the declared points_range (see the 2D kernel).
       const bool fits = rx >= 0 && rx + 8 <= TX && ry >= 0 && ry + NS + 1 <= TY && rz >= 0 && rz + NS + 1 <= TZ &&
                         ((rx | ry | rz) & 1) == 0;
