@@ -1,0 +1,29 @@
+"""Small transforms through every default kernel family (sweep spreaders 2D / 3D, quarter-warp
+interpolators, row-lane kernels 2D / 3D, generic 1D, set_points incl. the fingerprint) for
+compute-sanitizer (memcheck / racecheck / initcheck run this script)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import tensorflow_nufft_b200 as tfft
+from tests import helpers as H
+
+tfft.set_points_reuse(len(sys.argv) > 1 and sys.argv[1] == "reuse")
+cases = [((40, 36), 6000, 8, np.complex64, 1e-6), ((40, 36), 3000, 5, np.complex64, 1e-4), ((20, 24, 28), 8000, 1, np.complex64, 1e-6),
+         ((20, 24, 28), 4000, 2, np.complex64, 1e-3), ((24, 20), 2000, 2, np.complex128, 1e-12), ((12, 16, 10), 1500, 1, np.complex128, 1e-9),
+         ((16, 12, 14), 1500, 1, np.complex64, 1e-7), ((64,), 800, 2, np.complex64, 1e-6)]
+for grid, M, T, cd, tol in cases:
+  rank = len(grid)
+  rd = np.float32 if cd == np.complex64 else np.float64
+  pts = torch.from_numpy(H.uniform_points(M, rank, 3, rd)).cuda()
+  for tt in (1, 2):
+    src = torch.from_numpy(H.random_complex((T, M) if tt == 1 else (T,) + grid, 4, cd)).cuda()
+    for _ in range(2):
+      out = tfft.nufft(src, pts, grid_shape=grid, transform_type=f"type_{tt}", fft_direction="forward", tol=tol)
+    torch.cuda.synchronize()
+    assert torch.isfinite(torch.view_as_real(out)).all()
+f = torch.ones((2, 32, 48), dtype=torch.complex64, device="cuda")
+p2 = torch.from_numpy(H.uniform_points(3000, 2, 5) * np.float32(0.99)).cuda()
+tfft.interp(f, p2)
+tfft.spread(torch.ones((2, 3000), dtype=torch.complex64, device="cuda"), p2, (32, 48))
+torch.cuda.synchronize()
+print("sanitize script done")
