@@ -47,8 +47,8 @@ if __name__ == "__main__":
   if mode == "prof":
     run("cfg3", (128, 128, 128), H.uniform_points(8000000, 3, 3), 1, [dict(method=7)], reps=3)
     sys.exit(0)
-  V = [dict(method=2), dict(method=7), dict(method=7, otf_weights=2), dict(method=7, bins=(16, 8, 8)),
-       dict(method=7, no_preclear=1), dict(method=7, max_subproblem_size=4096), dict(method=7, no_preclear=1, bins=(16, 8, 32))]
+  V = [dict(method=2), dict(method=7), dict(method=7, bins=(8, 8, 16)), dict(method=7, bins=(8, 8, 8)),
+       dict(method=7, bins=(8, 8, 32)), dict(method=7, bins=(8, 16, 16)), dict(method=7, bins=(24, 8, 16))]
   run("cfg3-uniform-128^3-8M", (128, 128, 128), H.uniform_points(8000000, 3, 3), 1, V)
   run("cfg4adj-sos-256^3-4M", (256, 256, 256), H.stack_of_stars_points(125, 125, 256), 1, V[:4] + [dict(method=7, no_zrange=1)], reps=3)
   run("ref8-uniform-128^3-800k", (128, 128, 128), H.uniform_points(800000, 3, 18), 1, V[:4], reps=3)

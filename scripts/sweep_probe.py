@@ -47,9 +47,8 @@ if __name__ == "__main__":
   quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
   p = H.spiral_points(32, 62500)
   if len(sys.argv) > 1 and sys.argv[1] == "tune":
-    V = [dict(method=6), dict(method=6, bins=(32, 8)), dict(method=6, bins=(32, 16)), dict(method=6, bins=(16, 16)),
-         dict(method=6, bins=(48, 8)), dict(method=6, bins=(16, 4)), dict(method=6, bins=(32, 8), coils_per_cta=4),
-         dict(method=6, max_subproblem_size=512), dict(method=6, bins=(32, 8), max_subproblem_size=2048)]
+    V = [dict(method=6), dict(method=6, bins=(8, 8)), dict(method=6, bins=(8, 16)), dict(method=6, bins=(24, 8)),
+         dict(method=6, bins=(8, 8), coils_per_cta=16), dict(method=6, bins=(8, 4)), dict(method=6, bins=(8, 8), coils_per_cta=4)]
     run("cfg2-spiral-512-T32", (512, 512), p, 32, V, reps=5)
     run("uniform-512-T32", (512, 512), H.uniform_points(2000000, 2, 7), 32, V[:5], reps=3)
     sys.exit(0)

@@ -137,6 +137,7 @@ struct b200nufft_plan {
   RowLaneGeom rl{};        // row-lane 2D tile kernels (complex128; complex64 with ns > 7)
   int rl_pxt = 0, rl_lp = 0;
   bool adaptive_bin_z = false; // 3D type-2: bin depth chosen per point set (set_points)
+  bool adaptive_bin_x = false; // 3D sweep spreader: bin width chosen per point set (set_points)
   bool zrange_valid = false;   // sub_desc.w holds the z extent of every subproblem (3D interp plans)
   bool ws = false;         // window-sorted keys (type-1 register-accumulating spreader)
   bool ws2 = false;        // ... with even-row windows (spread_ws2.cuh): records carry a y shift
@@ -905,6 +906,18 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
       p->nbtot = p->nbins[0] * p->nbins[1] * p->nbins[2];
     }
   }
+  if (p->adaptive_bin_x && p->spread_method == 7) {
+    // 3D sweep spreader: narrow bins (8 x 8 x 16: 18 x 16-cell planes, 9 one-warp CTAs per SM instead of
+    // 7, shorter sweeps) when the point set is dense in the fine grid (cfg3, 0.48 points per cell: 1.19
+    // vs 1.29 ms), wide bins (16 x 8 x 16) when it is sparse (cfg4's set as type 1: 1.46 vs 1.66 ms;
+    // 800k points in 128^3: 0.46 vs 0.58 ms)
+    const int bx = static_cast<double>(M) > 0.25 * static_cast<double>(p->nftot) ? 8 : 16;
+    if (bx != p->bin[0]) {
+      p->bin[0] = bx;
+      p->nbins[0] = (p->nf[0] + bx - 1) / bx;
+      p->nbtot = p->nbins[0] * p->nbins[1] * p->nbins[2];
+    }
+  }
   // Buffers: a bound workspace must already hold M points; otherwise grow the plan's own buffers
   // (geometric headroom; b200nufft_reserve sizes them ahead of time so that this never allocates).
   if (p->ws_bound) {
@@ -1181,10 +1194,13 @@ int create_impl(b200nufft_plan* p) {
   }
   p->adaptive_bin_z = p->rank == 3 && p->type == 2 && !p->opts.spread_only && tile_ok && p->interp_method == 3 &&
                       p->opts.bin_dims[2] == 0 && p->bin[0] == 16 && p->bin[1] == 8;
+  p->adaptive_bin_x = p->rank == 3 && p->type == 1 && !p->opts.spread_only && p->spread_method == 7 &&
+                      p->opts.bin_dims[0] == 0 && p->bin[0] == 16;
   p->nb_max = p->nbtot;
   if (p->adaptive_bin_z) {   // set_points picks a bin depth of 2 or 8
     for (int bz : {2, 8}) p->nb_max = std::max(p->nb_max, p->nbins[0] * p->nbins[1] * ((p->nf[2] + bz - 1) / bz));
   }
+  if (p->adaptive_bin_x) p->nb_max = std::max(p->nb_max, ((p->nf[0] + 7) / 8) * p->nbins[1] * p->nbins[2]);
   p->msub = p->opts.max_subproblem_size > 0 ? p->opts.max_subproblem_size : 1024;  // refined per set_points
   const bool uses_tile = (p->type == 1 || p->opts.spread_only) ? p->spread_method >= 2 : false;
   p->ws = uses_tile && p->type == 1 && ws_any;
@@ -1215,8 +1231,11 @@ int create_impl(b200nufft_plan* p) {
       p->interp_method = 1;
     }
   } else if (uses_tile || uses_tile_i) {
-    if ((p->bin[0] % 16) != 0 || (p->bin[0] + 8) % 16 != 8)
-      return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels");
+    // tile pitch: bin_x + 8 = 8 (mod 16) cells for the round-1 tile kernels; the sweep spreaders need an
+    // ODD number of 16-byte cell pairs per row ((bin_x + 10) / 2), i.e. any multiple of 8
+    const bool sweep = uses_tile && (p->spread_method == 6 || p->spread_method == 7);
+    if (sweep ? (p->bin[0] % 8) != 0 : (p->bin[0] % 16) != 0)
+      return set_err(p, B200NUFFT_INVALID_ARGUMENT, "bin_dims[0] must be a multiple of 16 for the tile kernels (of 8 for the sweep spreaders)");
     size_t need = 0;
     if (uses_tile && p->spread_method == 6) need = std::max(need, spread_sweep2d_smem_bytes<4>(p->bin));
     else if (uses_tile && p->spread_method == 7) need = std::max(need, spread_sweep3d_smem_bytes(p->bin));

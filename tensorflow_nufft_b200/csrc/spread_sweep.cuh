@@ -19,8 +19,8 @@
 //     accumulator start (the accumulators have the tile's (re, im) layout: one 128-bit store and one
 //     128-bit load per coil, no adds, no dependent load-add-store chain).
 //   * Interior tiles leave through the TMA unit (cp.reduce.async.bulk.tensor add), as before.
-// The tile pitch is bin_x + 10 cells (= 2 mod 16), which makes the 8 row-lanes of a quarter warp
-// hit 8 distinct 16-byte bank groups.
+// The tile pitch is bin_x + 10 cells = an odd number of 16-byte cell pairs, which makes the 8
+// row-lanes of a quarter warp hit 8 distinct 16-byte bank groups.
 #pragma once
 #include <type_traits>
 
