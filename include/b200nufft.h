@@ -88,7 +88,8 @@ typedef struct b200nufft_opts {
                               fall back to 3 / 2 elsewhere                                        */
   int interp_method;       /* 0 auto, 1 point-driven from L2, 2 shared-memory tiles (TMA staged),
                               lanes over one point's stencil, 3 shared-memory tiles, quarter warp
-                              per point                                                           */
+                              per point, 7 (3D type-2 NUFFT plans, opt-in) quarter-warp gather from
+                              an 8-plane ring of the tile streamed along z                        */
   int profile;             /* 1: record CUDA events around the stages (b200nufft_get_timings)     */
   int upsampling;          /* fine-grid oversampling sigma: 0 = 2.0 (what Plan<GPUDevice> always uses,
                               nufft_plan.cu.cc:1855-1857); 1 = 1.25 (low-upsampling mode, width and

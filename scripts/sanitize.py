@@ -21,6 +21,14 @@ for grid, M, T, cd, tol in cases:
       out = tfft.nufft(src, pts, grid_shape=grid, transform_type=f"type_{tt}", fft_direction="forward", tol=tol)
     torch.cuda.synchronize()
     assert torch.isfinite(torch.view_as_real(out)).all()
+# dense 3D set (narrow sweep bins) and the opt-in ring interpolator
+from tensorflow_nufft_b200.python.ops import nufft_ops
+pd = torch.from_numpy(H.uniform_points(30000, 3, 9)).cuda()
+cd_ = torch.from_numpy(H.random_complex((1, 30000), 10)).cuda()
+tfft.nufft(cd_, pd, grid_shape=(16, 16, 16), transform_type="type_1")
+gd = torch.from_numpy(H.random_complex((2, 16, 20, 24), 11)).cuda()
+nufft_ops._run_op(gd, pd, (16, 20, 24), "type_2", "forward", 1e-6, None, "nufft", engine_kwargs={"interp_method": 7})
+torch.cuda.synchronize()
 f = torch.ones((2, 32, 48), dtype=torch.complex64, device="cuda")
 p2 = torch.from_numpy(H.uniform_points(3000, 2, 5) * np.float32(0.99)).cuda()
 tfft.interp(f, p2)

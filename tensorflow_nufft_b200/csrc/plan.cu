@@ -26,6 +26,7 @@
 #include "host_params.h"
 #include "interp.cuh"
 #include "interp_qw.cuh"
+#include "interp_ring.cuh"
 #include "rowlane.cuh"
 #include "points.cuh"
 #include "scan_sort.cuh"
@@ -590,6 +591,32 @@ cudaError_t launch_interp_qw(b200nufft_plan* p, int ntr, const float2* fw, float
   return cudaGetLastError();
 }
 
+cudaError_t launch_interp_ring3d(b200nufft_plan* p, int ntr, const float2* fw, float2* c, cudaStream_t st) {
+  GridGeom g = grid_geom(p);
+  const int64_t nblocks = p->sub_bound * ntr;
+  if (nblocks > 2147483647LL) return cudaErrorInvalidValue;
+  // one-plane TMA boxes: planes of (bin_x + 10) * (bin_y + 8) * 8 bytes must be a multiple of 128
+  const bool plane_ok = ((p->bin[0] + kQwHaloX) * (p->bin[1] + 8) * sizeof(float2)) % 128 == 0;
+  const int use_tma = (p->opts.reserved[0] == 0 && plane_ok &&
+                       ensure_tile_map(p, &p->tmap_in, fw, ntr, p->bin[0] + kQwHaloX, p->bin[1] + 8, 1, 1)) ? 1 : 0;
+  const size_t smem = interp_ring_smem_bytes(p->bin);
+#define RING_CASE(NS)                                                                            \
+  case NS: {                                                                                     \
+    auto k = interp_ring3d_f32_kernel<NS, kQwWarps>;                                             \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    k<<<static_cast<unsigned>(nblocks), kQwWarps * 32, smem, st>>>(p->M, g, ntr, p->sub_total(), \
+        p->sub_desc.as<int4>(), p->idx, p->start.as<int4>(), p->wrec.as<float4>(), fw, c, p->tmap_in.map, use_tma); \
+    break;                                                                                       \
+  }
+  switch (p->kp.ns) {
+    RING_CASE(2) RING_CASE(3) RING_CASE(4) RING_CASE(5) RING_CASE(6) RING_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef RING_CASE
+  return cudaGetLastError();
+}
+
 template <typename F>
 cudaError_t launch_interp_rowlane(b200nufft_plan* p, int ntr, const Cplx<F>* fw, Cplx<F>* c, cudaStream_t st) {
   GridGeom g = grid_geom(p);
@@ -720,6 +747,9 @@ int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t 
   if (p->interp_method == 5) {
     cudaError_t e = launch_interp_rowlane<F>(p, ntr, static_cast<const Cplx<F>*>(fw), static_cast<Cplx<F>*>(c), st);
     if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp rowlane launch: %s", cudaGetErrorString(e));
+  } else if (p->interp_method == 7) {
+    cudaError_t e = launch_interp_ring3d(p, ntr, static_cast<const float2*>(fw), static_cast<float2*>(c), st);
+    if (e != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "interp ring launch: %s", cudaGetErrorString(e));
   } else if (p->interp_method >= 3) {
     const float2* ff = static_cast<const float2*>(fw);
     float2* cc = static_cast<float2*>(c);
@@ -955,7 +985,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
     p->fp_layout = layout;
   }
 
-  BinGeom bg;
+  BinGeom bg{};
   bg.rank = rank;
   bg.rounding = 0;
   for (int d = 0; d < 3; ++d) { bg.nf[d] = p->nf[d]; bg.bin[d] = p->bin[d]; bg.nbins[d] = p->nbins[d]; }
@@ -972,7 +1002,9 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   bg.align_y = (p->ws2 || p->ws3) ? 1 : 0;
   bg.align_z = p->ws3 ? 1 : 0;
   bg.WZ = p->ws3 ? wmax_z : 1;
-  const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY * bg.WZ : 1);
+  bg.zkey = (p->interp_method == 7 && p->type == 2 && rank == 3) ? 1 : 0;
+  if (bg.zkey) bg.WZ = std::min(p->bin[2] + 9 - p->kp.ns, kRingMaxZ);   // stencil z starts per tile (interp_ring.cuh)
+  const int64_t key_space = static_cast<int64_t>(p->nbtot) * (p->ws ? bg.WX * bg.WY * bg.WZ : (bg.zkey ? bg.WZ : 1));
 
   if (skip) {
     clear_ints_kernel<<<grid_for(p->nbtot + 1, 256), 256, 0, st>>>(p->bin_sizes.as<int>(), p->nbtot + 1, skip);
@@ -1147,7 +1179,10 @@ int create_impl(b200nufft_plan* p) {
   p->spread_method = (p->opts.spread_method == 0) ? (tile_ok ? (p->rank == 2 ? 6 : 7) : 1) : p->opts.spread_method;
   // interpolator: 3 = quarter-warp gather (measured: cfg2-type2 0.56 vs 0.92 ms per 8 coils, cfg3-type2
   // 1.18 vs 1.61 ms, cfg4 2.0 vs 3.8 ms per 2 coils against the lanes-over-stencil tile kernel 2)
-  p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1) : std::min(p->opts.interp_method, 3);
+  p->interp_method = (p->opts.interp_method == 0) ? (tile_ok ? 3 : 1)
+                                                  : (p->opts.interp_method == 7 ? 7 : std::min(p->opts.interp_method, 3));
+  // 7: 3D ring interpolator (z-slab streaming), type-2 NUFFT plans only (its sort key carries the z start)
+  if (p->interp_method == 7 && (p->rank != 3 || p->type != 2 || p->opts.spread_only || !tile_ok)) p->interp_method = tile_ok ? 3 : 1;
   if (!tile_ok) { p->spread_method = 1; p->interp_method = 1; }
   // complex128, and complex64 with widths the float tile kernels do not cover (ns 8..15; e.g.
   // sigma = 1.25 at tol 1e-6 -> ns = 10), 2D and 3D: row-lane tile kernels (rowlane.cuh) unless the
@@ -1184,6 +1219,7 @@ int create_impl(b200nufft_plan* p) {
     if (p->type == 2 && p->interp_method == 3) def_bin[1] = 8;   // cfg3-type2 1.18 vs 1.35 ms at 16 x 16 x 2
     if (p->type == 1 && p->spread_method == 2) def_bin[1] = 8;   // cfg3 2.79 vs 3.01 ms at 16 x 16 x 2 (TMA flush)
     if (p->type == 1 && p->spread_method == 7) { def_bin[1] = 8; def_bin[2] = 16; }   // ring of 8 planes: depth is free
+    if (p->type == 2 && p->interp_method == 7) { def_bin[1] = 8; def_bin[2] = 16; }   // ring of 8 planes: depth is free
     if (rl_ok) { def_bin[0] = p->is_double ? 8 : 16; def_bin[1] = 8; def_bin[2] = 4; }   // tile = bin + ns + 1 per dim
   }
   p->nbtot = 1;
@@ -1241,7 +1277,8 @@ int create_impl(b200nufft_plan* p) {
     else if (uses_tile && p->spread_method == 7) need = std::max(need, spread_sweep3d_smem_bytes(p->bin));
     else if (uses_tile && ws_any) need = std::max(need, p->rank == 2 ? spread_ws_smem_bytes<2, 8>(p->bin) : spread_ws_smem_bytes<3, 1>(p->bin));
     else if (uses_tile) need = std::max(need, p->rank == 2 ? spread_tile_smem_bytes<2, 1>(p->bin) : spread_tile_smem_bytes<3, kSpreadWarps3D>(p->bin));
-    if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin, 8) : interp_qw_smem_bytes<3>(p->bin));
+    if (uses_tile_i && p->interp_method == 7) need = std::max(need, interp_ring_smem_bytes(p->bin));
+    else if (uses_tile_i && p->interp_method >= 3) need = std::max(need, p->rank == 2 ? interp_qw_smem_bytes<2>(p->bin, 8) : interp_qw_smem_bytes<3>(p->bin));
     else if (uses_tile_i) need = std::max(need, p->rank == 2 ? interp_tile_smem_bytes<2, kInterpWarps>(p->bin) : interp_tile_smem_bytes<3, kInterpWarps>(p->bin));
     p->tile_smem = need;
     if (p->tile_smem > 227 * 1024)
@@ -1679,7 +1716,7 @@ int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const v
                       int32_t* bin_start_out, int32_t* bin_sizes_out, void* stream) {
   if (rank < 1 || rank > 3 || M < 0) return B200NUFFT_INVALID_ARGUMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  BinGeom bg;
+  BinGeom bg{};
   bg.rank = rank;
   bg.rounding = rounding;
   int nbtot = 1;

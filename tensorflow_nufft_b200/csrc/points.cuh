@@ -67,6 +67,7 @@ struct BinGeom {
   int align_y;   // stencil y start aligned down to an even row (ws2 spreader): wy counts row pairs
   int align_z;   // 3D sweep spreader: z start aligned down to an even plane, key also carries the z window
   int WZ;
+  int zkey;      // 3D ring interpolator: key = bin * WZ + (stencil z start relative to the tile, clamped)
 };
 
 template <typename F>
@@ -139,6 +140,12 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
         key = key * g.WZ + wz;
       }
       key = key * (g.WX * g.WY) + wy * g.WX + wx;
+    }
+    if (g.zkey) {
+      const int i1z = static_cast<int>(ceil(sub_rn(x[2], half_width)));
+      int rz = i1z - (bd[2] * g.bin[2] - 4);
+      rz = rz < 0 ? 0 : (rz >= g.WZ ? g.WZ - 1 : rz);
+      key = key * g.WZ + rz;
     }
     // one 16 / 32-byte record per point: the record kernel gathers a point's coordinates through
     // the sort permutation, and three separate arrays cost three 32-byte sectors per point
