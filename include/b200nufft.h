@@ -105,7 +105,10 @@ typedef struct b200nufft_opts {
                               [1] coils per CTA of the 2D spreader / interpolator (1, 2, 4, 8, 16)
                               [2] 1: no pre-clear of the fine grid on the plan's internal stream
                               [3] 1: sweep spreaders use scalar FFMA instead of packed FFMA2
-                              [4] 1: single cuFFT 3D plan instead of the pruned three-plan scheme
+                              [4] FFT stage: 0 the engine's own pruned passes when eligible (complex64,
+                                  2D / 3D, power-of-two fine sizes 64..1024, x modes a multiple of 32),
+                                  else cuFFT; 1: one full cuFFT plan; 2: cuFFT only (3D: the pruned
+                                  three-plan scheme) + amplify / deconvolve kernels
                               [5] 1: flush spreader tiles with REDG instead of TMA reduce-add
                               [6] 1: 3D tiles move all their z-planes (no per-subproblem z range)
                               [7] 1: 2D sweep spreader gathers coil-major strengths (no point-major
@@ -128,6 +131,8 @@ typedef struct b200nufft_info {
   int64_t subproblem_bound; /* upper bound on subproblem count used for the launch grid     */
   int spread_method;       /* kernel family actually selected (values of opts.spread_method; 5 = row-lane tiles) */
   int interp_method;       /* ... (values of opts.interp_method; 5 = row-lane tiles)       */
+  int fft_method;          /* 0 none (spread-only), 1 one cuFFT plan, 2 cuFFT three-plan pruned scheme (3D),
+                              3 the engine's own pruned passes with amplify / deconvolve fused */
 } b200nufft_info;
 
 void b200nufft_default_opts(b200nufft_opts* opts);

@@ -59,6 +59,7 @@ class Info(ctypes.Structure):
       ("subproblem_bound", ctypes.c_int64),
       ("spread_method", ctypes.c_int),
       ("interp_method", ctypes.c_int),
+      ("fft_method", ctypes.c_int),
   ]
 
 
@@ -164,6 +165,7 @@ def make_opts(**opt_kwargs):
   opts = Opts()
   lib().b200nufft_default_opts(ctypes.byref(opts))
   reserved = {"no_tma": 0, "coils_per_cta": 1, "no_preclear": 2, "no_pack": 3, "full_fft": 4,
+              "fft_mode": 4,
               "no_tma_flush": 5, "no_zrange": 6, "no_point_major": 7, "otf_weights": 7}
   for k, v in opt_kwargs.items():
     if k == "bin_dims":

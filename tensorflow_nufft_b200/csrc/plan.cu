@@ -22,6 +22,7 @@
 
 #include "../../include/b200nufft.h"
 #include "deconv.cuh"
+#include "fft_pruned.cuh"
 #include "dev_common.cuh"
 #include "host_params.h"
 #include "interp.cuh"
@@ -158,6 +159,10 @@ struct b200nufft_plan {
   // 2D (x, y) transforms run on those planes only and a strided 1D transform does the z axis.
   cufftHandle fft_xy_lo = 0, fft_xy_hi = 0, fft_z = 0;
   bool pruned_fft = false;
+  // own pruned + fused FFT passes (fft_pruned.cuh): complex64, power-of-two fine sizes
+  bool own_fft = false;
+  DevBuf fft_tw[3];        // per-axis twiddle tables (fft_fill_twiddles)
+  DevBuf fft_rfac[3];      // reciprocals of the deconvolution factors, rounded once from double
   int zlo = 0, zhi = 0;
 
   int64_t M = 0;
@@ -780,6 +785,75 @@ int do_interp(b200nufft_plan* p, int ntr, const void* fw, void* c, cudaStream_t 
   return B200NUFFT_OK;
 }
 
+// The plan's FFT stage as pruned one-axis passes with the amplify / deconvolve step fused into the
+// pass that touches the mode array (fft_pruned.cuh). f: the batch's modes [ntr][N].
+struct FftDeviceExec {
+  b200nufft_plan* p;
+  int ntr;
+  float2* fw;
+  float2* f;
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+
+  template <int LOGN, int KIND>
+  void col_t(int axis, const FftColGeom& g, const float* pa, const float* po) {
+    auto k = fft_col_kernel<LOGN, KIND>;
+    const size_t smem = fft_col_smem_bytes(LOGN);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(static_cast<unsigned>(g.N0 >> fft_logw(LOGN)), static_cast<unsigned>(g.outer_count), static_cast<unsigned>(ntr));
+    k<<<grid, kFftColThreads, smem, st>>>(g, static_cast<float>(p->fft_sign), p->fft_tw[axis].as<float2>(), fw, f, pa, po,
+                                          p->fft_rfac[0].as<float>());
+    p->launches++;
+  }
+  template <int LOGN>
+  void col_k(int axis, int kind, const FftColGeom& g, const float* pa, const float* po) {
+    if (kind == kFftPlain) col_t<LOGN, kFftPlain>(axis, g, pa, po);
+    else if (kind == kFftFromModes) col_t<LOGN, kFftFromModes>(axis, g, pa, po);
+    else col_t<LOGN, kFftToModes>(axis, g, pa, po);
+  }
+  void col(int axis, int kind, const FftColGeom& g, int axis_a, int axis_o) {
+    const float* pa = axis_a >= 0 ? p->fft_rfac[axis_a].as<float>() : nullptr;
+    const float* po = axis_o >= 0 ? p->fft_rfac[axis_o].as<float>() : nullptr;
+    switch (fft_log2(p->nf[axis])) {
+      case 6: col_k<6>(axis, kind, g, pa, po); break;
+      case 7: col_k<7>(axis, kind, g, pa, po); break;
+      case 8: col_k<8>(axis, kind, g, pa, po); break;
+      case 9: col_k<9>(axis, kind, g, pa, po); break;
+      case 10: col_k<10>(axis, kind, g, pa, po); break;
+      default: err = cudaErrorInvalidValue;
+    }
+  }
+  template <int LOGN>
+  void row_t(const FftRowGeom& g, long long rows) {
+    auto k = fft_row_kernel<LOGN>;
+    const size_t smem = fft_row_smem_bytes(LOGN);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(static_cast<unsigned>(rows / fft_rows_per_cta(LOGN)), static_cast<unsigned>(ntr));
+    k<<<grid, kFftThreads, smem, st>>>(g, static_cast<float>(p->fft_sign), p->fft_tw[0].as<float2>(), fw);
+    p->launches++;
+  }
+  void row(const FftRowGeom& g, long long rows) {
+    switch (fft_log2(g.n0)) {
+      case 6: row_t<6>(g, rows); break;
+      case 7: row_t<7>(g, rows); break;
+      case 8: row_t<8>(g, rows); break;
+      case 9: row_t<9>(g, rows); break;
+      case 10: row_t<10>(g, rows); break;
+      default: err = cudaErrorInvalidValue;
+    }
+  }
+};
+
+int do_fft_own(b200nufft_plan* p, int ntr, float2* fw, float2* f, cudaStream_t st) {
+  FftDeviceExec ex{p, ntr, fw, f, st};
+  int N[3];
+  for (int d = 0; d < 3; ++d) N[d] = static_cast<int>(p->n_modes[d]);
+  fft_pruned_sequence(p->type, p->rank, p->nf, N, ex);
+  if (ex.err != cudaSuccess) return set_err(p, B200NUFFT_INTERNAL, "own FFT: unsupported size");
+  LAUNCH_OK(p);
+  return B200NUFFT_OK;
+}
+
 int do_fft(b200nufft_plan* p, int ntr, cudaStream_t st) {
   const int dir = p->fft_sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
   if (p->pruned_fft) {
@@ -871,22 +945,34 @@ int execute_impl(b200nufft_plan* p, void* c_, void* f_, cudaStream_t st) {
       int rc = do_spread<F>(p, ntr, cb, fw, st);
       if (rc) return rc;
       if (prof) cudaEventRecord(ev[1], st);
-      rc = do_fft(p, ntr, st);
-      if (rc) return rc;
-      if (prof) cudaEventRecord(ev[2], st);
-      dim3 grid(static_cast<unsigned>(p->n_modes_tot / p->n_modes[0]), ntr);
-      deconvolve_kernel<F><<<grid, std::min<int>(256, std::max<int>(32, ((int)p->n_modes[0] + 31) / 32 * 32)), 0, st>>>(mg, p1, p2, p3, fw, fb);
-      LAUNCH_OK(p);
-      p->launches++;
-      if (prof) cudaEventRecord(ev[3], st);
+      if (p->own_fft) {   // FFT passes, the last one divides by the factors and writes the modes
+        rc = do_fft_own(p, ntr, reinterpret_cast<float2*>(fw), reinterpret_cast<float2*>(fb), st);
+        if (rc) return rc;
+        if (prof) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
+      } else {
+        rc = do_fft(p, ntr, st);
+        if (rc) return rc;
+        if (prof) cudaEventRecord(ev[2], st);
+        dim3 grid(static_cast<unsigned>(p->n_modes_tot / p->n_modes[0]), ntr);
+        deconvolve_kernel<F><<<grid, std::min<int>(256, std::max<int>(32, ((int)p->n_modes[0] + 31) / 32 * 32)), 0, st>>>(mg, p1, p2, p3, fw, fb);
+        LAUNCH_OK(p);
+        p->launches++;
+        if (prof) cudaEventRecord(ev[3], st);
+      }
     } else {
       if (prof) cudaEventRecord(ev[0], st);
-      dim3 grid(static_cast<unsigned>((p->nftot / p->nf[0] + kAmplifyRowsPerCta - 1) / kAmplifyRowsPerCta), ntr);
-      amplify_kernel<F><<<grid, 32 * kAmplifyRowsPerCta, 0, st>>>(mg, p1, p2, p3, fb, fw);
-      LAUNCH_OK(p);
-      p->launches++;
-      if (prof) cudaEventRecord(ev[1], st);
-      int rc = do_fft(p, ntr, st);
+      int rc = 0;
+      if (p->own_fft) {   // the first FFT pass reads the modes and amplifies them: no fill of the fine grid
+        if (prof) cudaEventRecord(ev[1], st);
+        rc = do_fft_own(p, ntr, reinterpret_cast<float2*>(fw), reinterpret_cast<float2*>(fb), st);
+      } else {
+        dim3 grid(static_cast<unsigned>((p->nftot / p->nf[0] + kAmplifyRowsPerCta - 1) / kAmplifyRowsPerCta), ntr);
+        amplify_kernel<F><<<grid, 32 * kAmplifyRowsPerCta, 0, st>>>(mg, p1, p2, p3, fb, fw);
+        LAUNCH_OK(p);
+        p->launches++;
+        if (prof) cudaEventRecord(ev[1], st);
+        rc = do_fft(p, ntr, st);
+      }
       if (rc) return rc;
       if (prof) cudaEventRecord(ev[2], st);
       rc = do_interp<F>(p, ntr, fw, cb, st);
@@ -1301,7 +1387,25 @@ int create_impl(b200nufft_plan* p) {
     if (!p->opts.external_workspace)
       CUDA_OK(p, p->fine.reserve(p->mem, sizeof(Cplx<F>) * p->nftot * p->batch, false));
     const cufftType ftype = p->is_double ? CUFFT_Z2Z : CUFFT_C2C;
-    if (p->rank == 3 && p->opts.reserved[4] == 0) {
+    // reserved[4]: 0 = own pruned passes when eligible, else cuFFT (3D: pruned three-plan scheme);
+    // 1 = one full cuFFT plan; 2 = cuFFT only (3D: the three-plan scheme)
+    p->own_fft = !p->is_double && p->opts.reserved[4] == 0 && fft_pruned_ok(p->rank, p->nf, p->n_modes);
+    if (p->own_fft) {
+      for (int d = 0; d < p->rank; ++d) {
+        const int logn = fft_log2(p->nf[d]);
+        std::vector<float2> tw(fft_tw_count(logn) + 1);
+        fft_fill_twiddles(logn, p->fft_sign < 0 ? -1 : 1, tw.data());
+        CUDA_OK(p, p->fft_tw[d].reserve(p->mem, sizeof(float2) * tw.size(), false));
+        CUDA_OK(p, cudaMemcpy(p->fft_tw[d].p, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+        const int nc = p->nf[d] / 2 + 1;
+        std::vector<float> rf(nc);
+        const float* fs = reinterpret_cast<const float*>(p->fser_host[d].data());
+        for (int k = 0; k < nc; ++k) rf[k] = static_cast<float>(1.0 / static_cast<double>(fs[k]));
+        CUDA_OK(p, p->fft_rfac[d].reserve(p->mem, sizeof(float) * nc, false));
+        CUDA_OK(p, cudaMemcpy(p->fft_rfac[d].p, rf.data(), sizeof(float) * nc, cudaMemcpyHostToDevice));
+      }
+    }
+    if (!p->own_fft && p->rank == 3 && p->opts.reserved[4] != 1) {
       // modes k = -(n/2) .. (n-1)/2 live in fine planes [0, zlo) and [nf - zhi, nf)
       p->zlo = static_cast<int>((p->n_modes[2] - 1) / 2 + 1);
       p->zhi = static_cast<int>(p->n_modes[2] / 2);
@@ -1324,7 +1428,7 @@ int create_impl(b200nufft_plan* p) {
         p->pruned_fft = ok;
       }
     }
-    if (!p->pruned_fft) {
+    if (!p->pruned_fft && !p->own_fft) {
       int n[3];
       for (int d = 0; d < p->rank; ++d) n[d] = p->nf[p->rank - 1 - d];
       cufftResult r = cufftPlanMany(&p->fft, p->rank, n, nullptr, 1, 0, nullptr, 1, 0, ftype, p->batch);
@@ -1470,6 +1574,7 @@ void b200nufft_plan_destroy(b200nufft_plan* p) {
   if (p->fft_z) cufftDestroy(p->fft_z);
   for (DevBuf* b : p->ws_bufs()) b->release(p->mem);
   for (int d = 0; d < 3; ++d) p->fser[d].release(p->mem);
+  for (int d = 0; d < 3; ++d) { p->fft_tw[d].release(p->mem); p->fft_rfac[d].release(p->mem); }
   p->misc.release(p->mem);
   p->reuse.release(p->mem);
   if (p->h_flag) cudaFreeHost(p->h_flag);
@@ -1789,6 +1894,7 @@ int b200nufft_get_info(const b200nufft_plan* p, b200nufft_info* info) {
   info->subproblem_bound = p->sub_bound;
   info->spread_method = (p->type == 1 || p->opts.spread_only) ? p->spread_method : 0;
   info->interp_method = (p->type == 2 || p->opts.spread_only) ? p->interp_method : 0;
+  info->fft_method = p->opts.spread_only ? 0 : (p->own_fft ? 3 : (p->pruned_fft ? 2 : 1));
   return B200NUFFT_OK;
 }
 
