@@ -1,6 +1,8 @@
-"""Randomised differential test (GPU): default tile kernels vs the generic point-driven kernels
-(spread_method = interp_method = 1) on random ranks, grids, tolerances, coil counts, precisions
-and point distributions (uniform, clustered, on-grid, fold-boundary values)."""
+"""Randomised differential test (GPU): the default engine (tile kernels, own pruned FFT passes where
+eligible) vs the generic point-driven kernels (spread_method = interp_method = 1) with one full cuFFT
+plan (fft_mode = 1) on random ranks, grids (a third of them powers of two, so that the own FFT
+runs), tolerances, coil counts, precisions and point distributions (uniform, clustered, on-grid,
+fold-boundary values)."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -36,6 +38,9 @@ def main(n_cases, seed, gmax2=70, gmax3=28):
     rdtype = np.float32 if cdtype == np.complex64 else np.float64
     tol = float(rng.choice([1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7] if cdtype == np.complex64 else [1e-4, 1e-6, 1e-8, 1e-10, 1e-12, 1e-13]))
     grid = tuple(int(rng.integers(3, gmax2 if rank == 2 else gmax3)) for _ in range(rank))
+    if rng.random() < 0.33:   # power-of-two modes: fine sizes 64 .. 1024, the own FFT passes
+      grid = tuple(int(rng.choice([32, 64, 128, 256, 512] if rank == 2 else [32, 32, 64, 128])) for _ in range(rank))
+      if rank == 3 and np.prod(grid) > 64 * 64 * 64: grid = (32, 64, 32)
     M = int(rng.choice([1, 7, 33, 500, 5000, 30000]))
     T = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 16, 33]))
     if rank == 3: T = min(T, 5)
@@ -47,7 +52,7 @@ def main(n_cases, seed, gmax2=70, gmax3=28):
     for meth in (1, 0):
       out = nufft_ops._run_op(torch.from_numpy(src).cuda(), torch.from_numpy(pts).cuda(), grid, f"type_{ttype}",
                               "backward" if case % 2 else "forward", tol, None, "nufft",
-                              engine_kwargs={"spread_method": meth, "interp_method": meth})
+                              engine_kwargs={"spread_method": meth, "interp_method": meth, "fft_mode": meth})
       outs.append(out.cpu().numpy())
     err = H.rel_l2(outs[1], outs[0])
     # two float32 summation orders of up to M terms per cell (clustered points) differ by ~sqrt(M) ulp

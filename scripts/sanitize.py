@@ -1,5 +1,6 @@
 """Small transforms through every default kernel family (sweep spreaders 2D / 3D, quarter-warp
-interpolators, row-lane kernels 2D / 3D, generic 1D, set_points incl. the fingerprint) for
+interpolators, row-lane kernels 2D / 3D, generic 1D, set_points incl. the fingerprint, the own FFT
+passes of every length 64 .. 1024 on both kinds of axis) for
 compute-sanitizer (memcheck / racecheck / initcheck run this script)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +11,11 @@ from tests import helpers as H
 tfft.set_points_reuse(len(sys.argv) > 1 and sys.argv[1] == "reuse")
 cases = [((40, 36), 6000, 8, np.complex64, 1e-6), ((40, 36), 3000, 5, np.complex64, 1e-4), ((20, 24, 28), 8000, 1, np.complex64, 1e-6),
          ((20, 24, 28), 4000, 2, np.complex64, 1e-3), ((24, 20), 2000, 2, np.complex128, 1e-12), ((12, 16, 10), 1500, 1, np.complex128, 1e-9),
-         ((16, 12, 14), 1500, 1, np.complex64, 1e-7), ((64,), 800, 2, np.complex64, 1e-6)]
+         ((16, 12, 14), 1500, 1, np.complex64, 1e-7), ((64,), 800, 2, np.complex64, 1e-6),
+         # power-of-two fine grids: the own pruned FFT passes (rows: last axis, strided: the others)
+         ((32, 64), 2000, 3, np.complex64, 1e-6), ((128, 32), 2000, 1, np.complex64, 1e-6), ((32, 512), 1000, 1, np.complex64, 1e-6),
+         ((512, 32), 1000, 2, np.complex64, 1e-6), ((256, 256), 3000, 1, np.complex64, 1e-6),
+         ((32, 32, 32), 3000, 2, np.complex64, 1e-6), ((64, 32, 128), 3000, 1, np.complex64, 1e-6)]
 for grid, M, T, cd, tol in cases:
   rank = len(grid)
   rd = np.float32 if cd == np.complex64 else np.float64

@@ -46,7 +46,7 @@
 namespace b200 {
 
 constexpr int kFftThreads = 256;      // x pass: one item per thread
-constexpr int kFftColThreads = 512;   // strided passes: 2 CTAs per SM (64 registers: packed math needs aligned pairs)
+constexpr int kFftColThreads = 512;   // strided passes: 3 CTAs of 64 KB per SM = 48 warps (40 registers)
 constexpr int kFftMinLog = 6, kFftMaxLog = 10;
 // strided passes: columns per bundle: 16 (128-byte segments), 8 for n = 1024 (64 KB of shared memory)
 constexpr int fft_logw(int logn) { return logn >= 10 ? 3 : 4; }
@@ -416,7 +416,7 @@ FFT_HD void fft_col_last(const FftColGeom& g, const FftColCtx& cx, int o, int ti
   const FftPop pop = fft_pop(g.N, g.n, KIND == kFftToModes || g.out_pop);
   const float rt = KIND == kFftToModes ? fft_thread_factor(g, cx.k0g + c, o, ro, rx) : 0.f;
   const int half = g.N / 2;
-  for (int t = tid >> LOGW; t < A::T; t += nthr >> LOGW) {
+  for (int t = tid >> LOGW; t < A::T; t += nthr >> LOGW) {   // not unrolled: two items in flight spill at 40 registers
     float2 a[8];
     PH::last(s, tw, c, t, a, sg);
 #pragma unroll
@@ -571,7 +571,7 @@ inline int fft_log2(int n) {
 #if defined(__CUDACC__)
 // grid (N0 / W, outer_count, transforms); dynamic shared memory fft_col_smem_bytes(LOGN)
 template <int LOGN, int KIND>
-__global__ void __launch_bounds__(kFftColThreads, 2)
+__global__ void __launch_bounds__(kFftColThreads, 3)
 fft_col_kernel(FftColGeom g, float sg, const float2* __restrict__ tw, float2* fw, float2* f,
                const float* __restrict__ ra, const float* __restrict__ ro, const float* __restrict__ rx) {
   using A = FftAlg<LOGN>;
