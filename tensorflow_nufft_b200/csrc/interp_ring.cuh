@@ -39,7 +39,7 @@ interp_ring3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__
                          const int4* __restrict__ sub_desc, const int* __restrict__ idx,
                          const int4* __restrict__ start, const float4* __restrict__ wrec4 /*[M][6]*/,
                          const float2* __restrict__ fw, float2* __restrict__ c,
-                         const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                         const __grid_constant__ CUtensorMap tmap, int use_tma, int zrange) {
   constexpr int RING = kInterpRing;
   constexpr int C4 = 6;
   extern __shared__ __align__(128) float4 smem4[];
@@ -67,21 +67,6 @@ interp_ring3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__
   const bool interior = use_tma && ox >= 0 && ox + TX <= g.nf[0] && oy >= 0 && oy + TY <= g.nf[1] &&
                         oz >= 0 && oz + TZ <= g.nf[2];
   const int WZ = min(TZ - NS + 1, kRingMaxZ);   // admissible stencil starts 0 .. WZ - 1
-
-  // ---- group table: points per stencil start (the points are sorted by it) ----
-  for (int i = tid; i < kRingMaxZ + 1; i += WARPS * 32) goff[i] = 0;
-  if (interior && tid < RING) mbar_init(bars + tid, 1);
-  __syncthreads();
-  for (int i = tid; i < np; i += WARPS * 32) {
-    const int rz = start[p0 + i].z - oz;
-    atomicAdd(&goff[min(max(rz, 0), WZ - 1) + 1], 1);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int i = 1; i <= WZ; ++i) { run += goff[i]; goff[i] = run; }   // goff[rz + 1] = end of group rz
-  }
-  __syncthreads();
 
   // ---- plane loads ----
   // mbarrier phases per slot (every thread keeps the same masks): next_par = parity the slot's next
@@ -111,9 +96,35 @@ interp_ring3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__
     }
   };
 
+  for (int i = tid; i < kRingMaxZ + 1; i += WARPS * 32) goff[i] = 0;
+  if (interior && tid < RING) mbar_init(bars + tid, 1);
+  __syncthreads();
+  // The first ring of planes leaves BEFORE the group table is built: the smallest stencil start of
+  // the subproblem is already in its descriptor (subproblem_zrange_kernel), so the tile's first
+  // 8 planes and the table's pass over start[] are one global round trip, not two.
+  int issued_hi = 0;   // planes below this have been issued (monotone)
+  if (zrange) {
+    const int lo = (sd.w & 0xffff) - 32768 - oz;
+    if (lo >= 0 && lo < WZ) {
+      for (int z = lo; z < min(lo + RING, TZ); ++z) issue_plane(z);
+      issued_hi = min(lo + RING, TZ);
+    }
+  }
+
+  // ---- group table: points per stencil start (the points are sorted by it) ----
+  for (int i = tid; i < np; i += WARPS * 32) {
+    const int rz = start[p0 + i].z - oz;
+    atomicAdd(&goff[min(max(rz, 0), WZ - 1) + 1], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 1; i <= WZ; ++i) { run += goff[i]; goff[i] = run; }   // goff[rz + 1] = end of group rz
+  }
+  __syncthreads();
+
   const int pt = lane >> 3;
   const int row = lane & 7;
-  int issued_hi = 0;   // planes below this have been issued (monotone)
   for (int rz = 0; rz < WZ; ++rz) {
     const int gbeg = goff[rz], gend = goff[rz + 1];
     if (gend == gbeg) continue;   // uniform over the CTA

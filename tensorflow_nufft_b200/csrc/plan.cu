@@ -611,7 +611,8 @@ cudaError_t launch_interp_ring3d(b200nufft_plan* p, int ntr, const float2* fw, f
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     k<<<static_cast<unsigned>(nblocks), kQwWarps * 32, smem, st>>>(p->M, g, ntr, p->sub_total(), \
-        p->sub_desc.as<int4>(), p->idx, p->start.as<int4>(), p->wrec.as<float4>(), fw, c, p->tmap_in.map, use_tma); \
+        p->sub_desc.as<int4>(), p->idx, p->start.as<int4>(), p->wrec.as<float4>(), fw, c, p->tmap_in.map, use_tma, \
+        (p->zrange_valid && p->opts.reserved[6] == 0) ? 1 : 0); \
     break;                                                                                       \
   }
   switch (p->kp.ns) {
@@ -1173,7 +1174,7 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   if (!p->otf) p->launches++;
 
   p->zrange_valid = false;
-  const bool zr_interp = p->interp_method == 3 && (p->type == 2 || p->opts.spread_only);
+  const bool zr_interp = (p->interp_method == 3 || p->interp_method == 7) && (p->type == 2 || p->opts.spread_only);
   const bool zr_spread = p->spread_method == 2 && (p->type == 1 || p->opts.spread_only);
   if (rank == 3 && !p->is_double && (zr_interp || zr_spread) && p->sub_bound > 0) {
     subproblem_zrange_kernel<<<ceil_div(p->sub_bound, 8), 256, 0, st>>>(p->sub_total(), p->start.as<int4>(),
