@@ -59,6 +59,31 @@ __device__ __forceinline__ float qw_reduce(float (&v)[N], int lane) {
   return v[0];
 }
 
+// One stencil row of 8 complex cells (four float4 = cells 0..7 as (re, im) pairs) times the 8
+// x-weights: (re, im) += w * (cell.re, cell.im) as ONE packed FFMA2 per cell (fma.rn.f32x2, the
+// weight rides in the scalar-broadcast operand) instead of two FFMA. Same products, same order.
+__device__ __forceinline__ void qw_fma2(float& re, float& im, float w, float cr, float ci) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "mov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(re), "+f"(im) : "f"(w), "f"(cr), "f"(ci));
+}
+__device__ __forceinline__ void qw_row_dot(const float4& v0, const float4& v1, const float4& v2, const float4& v3,
+                                           const float4& xa, const float4& xb, float& pr, float& pi) {
+  pr = v0.x * xa.x;
+  pi = v0.y * xa.x;
+  qw_fma2(pr, pi, xa.y, v0.z, v0.w);
+  qw_fma2(pr, pi, xa.z, v1.x, v1.y);
+  qw_fma2(pr, pi, xa.w, v1.z, v1.w);
+  qw_fma2(pr, pi, xb.x, v2.x, v2.y);
+  qw_fma2(pr, pi, xb.y, v2.z, v2.w);
+  qw_fma2(pr, pi, xb.z, v3.x, v3.y);
+  qw_fma2(pr, pi, xb.w, v3.z, v3.w);
+}
+
 // Gathers the points [0, np) of one subproblem from NC coil tiles (`tile4`, tile k at offset
 // k * ncell / 2 float4; origin ox, oy, oz; pitch TX cells). Groups of 4 points are dealt
 // round-robin to the `nwarps` warps. Records are read from global memory (sorted order, base
@@ -140,18 +165,16 @@ __device__ __forceinline__ void qw_gather(WaitTile&& wait_tile, const float4* __
         float re = 0.f, im = 0.f;
         if (RANK == 2) {
           const float4 v0 = pk[0], v1 = pk[1], v2 = pk[2], v3 = pk[3];
-          re = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
-          im = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
+          qw_row_dot(v0, v1, v2, v3, xa, xb, re, im);
         } else {
           const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
           for (int dz = 0; dz < NS; ++dz) {
             const float4* pz = pk + dz * zstride4;
             const float4 v0 = pz[0], v1 = pz[1], v2 = pz[2], v3 = pz[3];
-            const float pr = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
-            const float pi = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
-            re += wz[dz] * pr;
-            im += wz[dz] * pi;
+            float pr, pi;
+            qw_row_dot(v0, v1, v2, v3, xa, xb, pr, pi);
+            qw_fma2(re, im, wz[dz], pr, pi);
           }
         }
         v[2 * k] = re * wy_c;

@@ -165,10 +165,9 @@ interp_ring3d_f32_kernel(int64_t M, GridGeom g, int ntr, const int* __restrict__
           for (int dz = 0; dz < NS; ++dz) {
             const float4* pz = ring + ((rz + dz) & (RING - 1)) * plane4 + rowoff;
             const float4 v0 = pz[0], v1 = pz[1], v2 = pz[2], v3 = pz[3];
-            const float pr = v0.x * xa.x + v0.z * xa.y + v1.x * xa.z + v1.z * xa.w + v2.x * xb.x + v2.z * xb.y + v3.x * xb.z + v3.z * xb.w;
-            const float pi = v0.y * xa.x + v0.w * xa.y + v1.y * xa.z + v1.w * xa.w + v2.y * xb.x + v2.w * xb.y + v3.y * xb.z + v3.w * xb.w;
-            re += wz[dz] * pr;
-            im += wz[dz] * pi;
+            float pr, pi;
+            qw_row_dot(v0, v1, v2, v3, xa, xb, pr, pi);
+            qw_fma2(re, im, wz[dz], pr, pi);
           }
           re *= wy;
           im *= wy;
