@@ -167,7 +167,7 @@ struct b200nufft_plan {
 
   int64_t M = 0;
   bool points_set = false;
-  DevBuf folded, keys0, keys1, vals0, vals1, hist, start, wrec;
+  DevBuf folded, keys0, pairs0, pairs1, idxbuf, hist, start, wrec;   // sort: keys, two (key, index) pair buffers, sorted indices
   DevBuf bin_sizes, bin_start, num_sub, sub_start, sub_desc, misc;  // misc: scan tmp[1024] + sub_total + range flag
   DevBuf reuse;            // ReuseState (opts.reuse_points)
   DevBuf ct;               // point-major strengths [M][batch] of the running batch (2D sweep spreader)
@@ -196,7 +196,7 @@ struct b200nufft_plan {
   // plan cache bookkeeping (b200nufft_plan_acquire / _release)
   bool from_cache = false;
   std::string cache_key;
-  int* idx = nullptr;      // points at vals0 or vals1
+  int* idx = nullptr;      // idxbuf once points are set
   int64_t sub_bound = 0;
   int* h_flag = nullptr;   // pinned
 
@@ -216,7 +216,7 @@ struct b200nufft_plan {
   const int* skip_flag() const { return opts.reuse_points ? &reuse.as<ReuseState>()->skip : nullptr; }
   // buffers that live in the caller's workspace when one is bound
   std::vector<DevBuf*> ws_bufs() {
-    return {&fine, &bin_sizes, &bin_start, &num_sub, &sub_start, &folded, &keys0, &keys1, &vals0, &vals1,
+    return {&fine, &bin_sizes, &bin_start, &num_sub, &sub_start, &folded, &keys0, &pairs0, &pairs1, &idxbuf,
             &hist, &start, &wrec, &sub_desc, &ct};
   }
 };
@@ -298,8 +298,9 @@ void ws_sizes(const b200nufft_plan* p, int64_t M, size_t out[kNumWsBufs]) {
   out[0] = p->opts.spread_only ? 0 : sizeof(Cplx<F>) * static_cast<size_t>(p->nftot) * p->batch;
   out[1] = out[2] = out[3] = out[4] = bins;
   out[5] = sizeof(F) * 4 * m;
-  out[6] = out[7] = sizeof(uint32_t) * m;
-  out[8] = out[9] = sizeof(int) * m;
+  out[6] = sizeof(uint32_t) * m;
+  out[7] = out[8] = sizeof(uint2) * m;
+  out[9] = sizeof(int) * m;
   out[10] = sizeof(int) * radix_hist_ints(m);
   out[11] = p->otf ? 0 : sizeof(int4) * m;
   out[12] = p->otf ? 0 : sizeof(F) * m * p->R;
@@ -1105,18 +1106,16 @@ int set_points_impl(b200nufft_plan* p, int64_t M, int layout, const void* x, con
   fold_key_kernel<F><<<grid_for(M, 256, 8), 256, 0, st>>>(
       M, layout, static_cast<const F*>(x), static_cast<const F*>(y), static_cast<const F*>(z),
       p->opts.points_range, check, lo, hi, bg, static_cast<F>(p->kp.half_width), p->folded.as<F>(),
-      p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->bin_sizes.as<int>(),
+      p->keys0.as<uint32_t>(), p->bin_sizes.as<int>(),
       p->range_flag(), skip);
   LAUNCH_OK(p);
   p->launches++;
 
-  uint32_t* ks;
-  int* vs;
-  p->launches += radix_sort_pairs(p->keys0.as<uint32_t>(), p->vals0.as<int>(), p->keys1.as<uint32_t>(),
-                                  p->vals1.as<int>(), M, ilog2_ceil(key_space), p->hist.as<int>(),
-                                  p->scan_tmp(), &ks, &vs, st, skip);
+  p->launches += radix_sort_index(p->keys0.as<uint32_t>(), p->pairs0.as<uint2>(), p->pairs1.as<uint2>(),
+                                  p->idxbuf.as<int>(), M, ilog2_ceil(key_space), p->hist.as<int>(),
+                                  p->scan_tmp(), st, skip);
   LAUNCH_OK(p);
-  p->idx = vs;
+  p->idx = p->idxbuf.as<int>();
 
   // Points per subproblem: the reference caps at 1024 (gpu_max_subproblem_size, nufft_options.h:153).
   // Small point sets get smaller subproblems so that the launch still fills the 148 SMs.
@@ -1833,25 +1832,24 @@ int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const v
     nbtot *= bg.nbins[d];
   }
   if (cudaMemsetAsync(bin_sizes_out, 0, sizeof(int) * nbtot, st) != cudaSuccess) return B200NUFFT_INTERNAL;
-  DevBuf k0, k1, v0, v1, hist, tmp;
+  DevBuf k0, pa, pb, v1, hist, tmp;
   MemCtx mem;
   cudaGetDevice(&mem.device);
   int rc = B200NUFFT_OK;
   if (M > 0) {
-    if (k0.reserve(mem, 4 * M) || k1.reserve(mem, 4 * M) || v0.reserve(mem, 4 * M) || v1.reserve(mem, 4 * M) ||
+    if (k0.reserve(mem, 4 * M) || pa.reserve(mem, 8 * M) || pb.reserve(mem, 8 * M) || v1.reserve(mem, 4 * M) ||
         hist.reserve(mem, sizeof(int) * radix_hist_ints(M)) || tmp.reserve(mem, sizeof(int) * (kScanMaxBlocks + 8))) {
       rc = B200NUFFT_RESOURCE_EXHAUSTED;
     } else {
       if (is_double)
         key_only_kernel<double><<<grid_for(M, 256), 256, 0, st>>>(M, (const double*)x, (const double*)y, (const double*)z, bg,
-                                                                 k0.as<uint32_t>(), v0.as<int>(), bin_sizes_out);
+                                                                 k0.as<uint32_t>(), bin_sizes_out);
       else
         key_only_kernel<float><<<grid_for(M, 256), 256, 0, st>>>(M, (const float*)x, (const float*)y, (const float*)z, bg,
-                                                                k0.as<uint32_t>(), v0.as<int>(), bin_sizes_out);
-      uint32_t* ks; int* vs;
-      radix_sort_pairs(k0.as<uint32_t>(), v0.as<int>(), k1.as<uint32_t>(), v1.as<int>(), M, ilog2_ceil(nbtot),
-                       hist.as<int>(), tmp.as<int>(), &ks, &vs, st);
-      cudaMemcpyAsync(idx_out, vs, sizeof(int) * M, cudaMemcpyDeviceToDevice, st);
+                                                                k0.as<uint32_t>(), bin_sizes_out);
+      radix_sort_index(k0.as<uint32_t>(), pa.as<uint2>(), pb.as<uint2>(), v1.as<int>(), M, ilog2_ceil(nbtot),
+                       hist.as<int>(), tmp.as<int>(), st);
+      cudaMemcpyAsync(idx_out, v1.as<int>(), sizeof(int) * M, cudaMemcpyDeviceToDevice, st);
     }
   } else {
     tmp.reserve(mem, sizeof(int) * (kScanMaxBlocks + 8));
@@ -1860,7 +1858,7 @@ int b200nufft_binsort(int is_double, int rank, int64_t M, const void* x, const v
     exclusive_scan_i32(bin_sizes_out, bin_start_out, nbtot, tmp.as<int>(), nullptr, st);
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200NUFFT_INTERNAL;
   }
-  k0.release(mem); k1.release(mem); v0.release(mem); v1.release(mem); hist.release(mem); tmp.release(mem);
+  k0.release(mem); pa.release(mem); pb.release(mem); v1.release(mem); hist.release(mem); tmp.release(mem);
   return rc;
 }
 

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256)
 fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __restrict__ p1,
                 const F* __restrict__ p2, int range, int check, F lo, F hi, BinGeom g, F half_width,
                 F* __restrict__ folded /* [M][4]: x, y, z, 0 */,
-                uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes,
+                uint32_t* __restrict__ keys, int* __restrict__ bin_sizes,
                 int* __restrict__ range_flag, const int* __restrict__ skip) {
   if (skip != nullptr && *skip) return;   // same point set as the last call (opts.reuse_points)
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -151,7 +151,6 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
     // the sort permutation, and three separate arrays cost three 32-byte sectors per point
     store_coords(folded + 4 * i, x[0], x[1], x[2]);
     keys[i] = static_cast<uint32_t>(key);
-    vals[i] = static_cast<int>(i);
     // Warp-aggregated histogram: one atomic per distinct bin per warp (hot bins, e.g. the
     // k-space centre of a radial trajectory, would otherwise serialise).
     const unsigned active = __activemask();
@@ -166,14 +165,13 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
 template <typename F>
 __global__ void __launch_bounds__(256)
 key_only_kernel(int64_t M, const F* __restrict__ f0, const F* __restrict__ f1, const F* __restrict__ f2,
-                BinGeom g, uint32_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bin_sizes) {
+                BinGeom g, uint32_t* __restrict__ keys, int* __restrict__ bin_sizes) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
     int key = bin_of<F>(f0[i], g.bin[0], g.nbins[0], g.rounding);
     if (g.rank > 1) key += g.nbins[0] * bin_of<F>(f1[i], g.bin[1], g.nbins[1], g.rounding);
     if (g.rank > 2) key += g.nbins[0] * g.nbins[1] * bin_of<F>(f2[i], g.bin[2], g.nbins[2], g.rounding);
     keys[i] = static_cast<uint32_t>(key);
-    vals[i] = static_cast<int>(i);
     const unsigned active = __activemask();
     const unsigned peers = __match_any_sync(active, key);
     const int leader = __ffs(peers) - 1;
@@ -477,13 +475,17 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
     const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
     const F x1 = sub_rn(static_cast<F>(i1), x);
     const int shift = ((align >> d) & 1) ? (i1 & 1) : 0;
-    F w[8];
+    // Seven evaluations (taps 0 .. 6 of the stencil; ns <= 7 here, taps t >= ns lie outside the support
+    // and evaluate to exactly 0), placed at slot t + shift: the eighth slot of the padded record is
+    // the zero the shifted / unshifted layout leaves free. No per-lane branch, no wasted evaluation.
+    F e[7];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      // Taps t < 0 and t >= ns lie outside the support (x1 in [-ns/2, -ns/2 + 1)) and evaluate
-      // to exactly 0: no per-lane condition, no divergence between lanes with different shifts.
-      w[k] = es_eval_fast<F>(add_rn(x1, static_cast<F>(k - shift)), beta, c, half_width);
-    }
+    for (int t = 0; t < 7; ++t) e[t] = es_eval_fast<F>(add_rn(x1, static_cast<F>(t)), beta, c, half_width);
+    F w[8];
+    w[0] = shift ? F(0) : e[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) w[k] = shift ? e[k - 1] : e[k];
+    w[7] = shift ? e[6] : F(0);
     F* out = wrec + g * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) out[k] = w[k];

@@ -167,9 +167,12 @@ inline int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stable LSD radix sort, 8- or 10-bit digits, (uint32 key, int32 value) pairs. Tile = 8 warps x 256
-// consecutive elements per warp; a warp walks its 256 elements in 8 rounds of 32 lanes, so the
-// (warp, round, lane) order IS the element order and ranks are stable by construction.
+// Stable LSD radix sort of the INDICES 0 .. n-1 by 32-bit keys, 8- or 10-bit digits. Tile = 8 warps
+// x 256 consecutive elements per warp; a warp walks its 256 elements in 8 rounds of 32 lanes, so
+// the (warp, round, lane) order IS the element order and ranks are stable by construction.
+// Data movement per pass (round 2): the first pass reads only the keys (the value of element i is
+// i), passes in between move (key, index) as ONE 8-byte pair -- one scattered store per element
+// instead of two -- and the last pass writes only the index (the sorted keys are never read).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSortWarps = 8;
 constexpr int kSortThreads = kSortWarps * 32;
@@ -178,9 +181,10 @@ constexpr int kSortPerWarp = 32 * kSortRounds;             // 256
 constexpr int kSortTile = kSortWarps * kSortPerWarp;       // 2048
 constexpr int kRadixBitsMax = 11;                          // 8-bit digits, or 10 / 11-bit when that saves a pass
 
-template <int BITS>
+// IN_PAIRS: the pass reads (key, index) pairs, else bare keys
+template <int BITS, bool IN_PAIRS>
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblk,
+radix_hist_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict__ pairs, int64_t n, int shift, int nblk,
                   int* __restrict__ hist /*[1 << BITS][nblk]*/, const int* __restrict__ skip) {
   if (skip != nullptr && *skip) return;
   constexpr int RADIX = 1 << BITS;
@@ -191,16 +195,17 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int n
 #pragma unroll
   for (int r = 0; r < kSortTile / kSortThreads; ++r) {
     int64_t i = base + r * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & (RADIX - 1)], 1);
+    if (i < n) atomicAdd(&cnt[((IN_PAIRS ? pairs[i].x : keys[i]) >> shift) & (RADIX - 1)], 1);
   }
   __syncthreads();
   for (int d = threadIdx.x; d < RADIX; d += kSortThreads) hist[static_cast<int64_t>(d) * nblk + blockIdx.x] = cnt[d];
 }
 
-template <int BITS>
+// OUT_PAIRS: the pass writes (key, index) pairs, else (last pass) the indices only
+template <int BITS, bool IN_PAIRS, bool OUT_PAIRS>
 __global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int64_t n,
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint2* __restrict__ pairs_in,
+                     uint2* __restrict__ pairs_out, int* __restrict__ idx_out, int64_t n,
                      int shift, int nblk, const int* __restrict__ offs /*[1 << BITS][nblk] scanned*/,
                      const int* __restrict__ skip) {
   if (skip != nullptr && *skip) return;
@@ -222,8 +227,14 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
   for (int r = 0; r < kSortRounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     const bool ok = i < n;
-    key[r] = ok ? keys_in[i] : 0xffffffffu;
-    val[r] = ok ? vals_in[i] : 0;
+    if (IN_PAIRS) {
+      const uint2 kv = ok ? pairs_in[i] : make_uint2(0xffffffffu, 0u);
+      key[r] = kv.x;
+      val[r] = static_cast<int>(kv.y);
+    } else {
+      key[r] = ok ? keys_in[i] : 0xffffffffu;
+      val[r] = static_cast<int>(i);
+    }
     // Invalid lanes use digit RADIX (out of range) so they never match a real digit.
     const unsigned dig = ok ? ((key[r] >> shift) & (RADIX - 1)) : RADIX;
     const unsigned peers = __match_any_sync(0xffffffffu, dig);
@@ -253,48 +264,65 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict
     if (i < n) {
       const unsigned dig = (key[r] >> shift) & (RADIX - 1);
       const int64_t pos = static_cast<int64_t>(gbase[dig]) + cnt[warp][dig] + rank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = val[r];
+      if (OUT_PAIRS) pairs_out[pos] = make_uint2(key[r], static_cast<uint32_t>(val[r]));
+      else idx_out[pos] = val[r];
     }
   }
 }
 
-// Sorts n pairs by the low `key_bits` bits of the key. Buffers: (k0,v0) hold the input; (k1,v1)
-// are scratch of the same size; hist holds kRadix*nblk ints; scan_tmp kScanMaxBlocks ints.
-// On return *keys_sorted/*vals_sorted point at whichever buffer holds the result.
-inline int radix_sort_pairs(uint32_t* k0, int* v0, uint32_t* k1, int* v1, int64_t n, int key_bits,
-                            int* hist, int* scan_tmp, uint32_t** keys_sorted, int** vals_sorted,
-                            cudaStream_t stream, const int* skip = nullptr) {
+__global__ void __launch_bounds__(256)
+iota_kernel(int* __restrict__ out, int64_t n, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = static_cast<int>(i);
+}
+
+template <int BITS>
+inline void radix_pass(const uint32_t* keys, const uint2* pin, uint2* pout, int* idx_out, bool first, bool last,
+                       int64_t n, int shift, int nblk, int* hist, int* scan_tmp, cudaStream_t stream, const int* skip,
+                       int* launches) {
+  if (first) radix_hist_kernel<BITS, false><<<nblk, kSortThreads, 0, stream>>>(keys, nullptr, n, shift, nblk, hist, skip);
+  else radix_hist_kernel<BITS, true><<<nblk, kSortThreads, 0, stream>>>(nullptr, pin, n, shift, nblk, hist, skip);
+  *launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << BITS) * nblk, scan_tmp, nullptr, stream, skip);
+  if (first && last) radix_scatter_kernel<BITS, false, false><<<nblk, kSortThreads, 0, stream>>>(keys, nullptr, nullptr, idx_out, n, shift, nblk, hist, skip);
+  else if (first) radix_scatter_kernel<BITS, false, true><<<nblk, kSortThreads, 0, stream>>>(keys, nullptr, pout, nullptr, n, shift, nblk, hist, skip);
+  else if (last) radix_scatter_kernel<BITS, true, false><<<nblk, kSortThreads, 0, stream>>>(nullptr, pin, nullptr, idx_out, n, shift, nblk, hist, skip);
+  else radix_scatter_kernel<BITS, true, true><<<nblk, kSortThreads, 0, stream>>>(nullptr, pin, pout, nullptr, n, shift, nblk, hist, skip);
+  *launches += 1;
+}
+
+// idx_out[j] = index of the element with the j-th smallest key (low `key_bits` bits; ties keep the
+// element order). pa / pb: scratch for n (key, index) pairs each (pb only when there are more than
+// two passes); hist holds radix_hist_ints(n) ints; scan_tmp kScanMaxBlocks ints. Returns the number
+// of kernels launched.
+inline int radix_sort_index(const uint32_t* keys, uint2* pa, uint2* pb, int* idx_out, int64_t n, int key_bits,
+                            int* hist, int* scan_tmp, cudaStream_t stream, const int* skip = nullptr) {
   int launches = 0;
-  uint32_t* kin = k0; int* vin = v0; uint32_t* kout = k1; int* vout = v1;
-  if (n > 0) {
-    const int nblk = static_cast<int>((n + kSortTile - 1) / kSortTile);
-    // 8-bit digits unless 10-bit digits save a whole pass (cfg2: 20 key bits -> 2 passes of 10).
-    // 11-bit digits (instantiated, off): cfg3's 22-bit window keys in 2 passes instead of 3 were
-    // measured SLOWER (set_points 1.26 vs 1.16 ms): the 2048-entry per-block tables and the 8x larger
-    // histogram scan cost more than the pass they save.
-    int bits = 8;
-    int passes = key_bits <= 0 ? 0 : (key_bits + 7) / 8;
-    for (int b2 : {10}) {
-      const int pb = key_bits <= 0 ? 0 : (key_bits + b2 - 1) / b2;
-      if (pb < passes) { passes = pb; bits = b2; }
-    }
-    for (int p = 0; p < passes; ++p) {
-      const int shift = p * bits;
-      if (bits == 11) radix_hist_kernel<11><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
-      else if (bits == 10) radix_hist_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
-      else radix_hist_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, nblk, hist, skip);
-      launches += 1 + exclusive_scan_i32(hist, hist, (static_cast<int64_t>(1) << bits) * nblk, scan_tmp, nullptr, stream, skip);
-      if (bits == 11) radix_scatter_kernel<11><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
-      else if (bits == 10) radix_scatter_kernel<10><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
-      else radix_scatter_kernel<8><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, nblk, hist, skip);
-      launches += 1;
-      std::swap(kin, kout);
-      std::swap(vin, vout);
-    }
+  if (n <= 0) return 0;
+  const int nblk = static_cast<int>((n + kSortTile - 1) / kSortTile);
+  // 8-bit digits unless 10-bit digits save a whole pass (cfg2: 20 key bits -> 2 passes of 10).
+  // 11-bit digits (instantiated for the histogram sizing only, off): cfg3's 22-bit window keys in 2
+  // passes instead of 3 were measured SLOWER (set_points 1.26 vs 1.16 ms): the 2048-entry per-block
+  // tables and the 8x larger histogram scan cost more than the pass they save.
+  int bits = 8;
+  int passes = key_bits <= 0 ? 0 : (key_bits + 7) / 8;
+  {
+    const int pb10 = key_bits <= 0 ? 0 : (key_bits + 9) / 10;
+    if (pb10 < passes) { passes = pb10; bits = 10; }
   }
-  *keys_sorted = kin;
-  *vals_sorted = vin;
+  if (passes == 0) {
+    iota_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, stream>>>(idx_out, n, skip);
+    return 1;
+  }
+  const uint2* pin = nullptr;
+  uint2* pout = pa;
+  for (int p = 0; p < passes; ++p) {
+    const bool first = p == 0, last = p == passes - 1;
+    if (bits == 10) radix_pass<10>(keys, pin, pout, idx_out, first, last, n, p * bits, nblk, hist, scan_tmp, stream, skip, &launches);
+    else radix_pass<8>(keys, pin, pout, idx_out, first, last, n, p * bits, nblk, hist, scan_tmp, stream, skip, &launches);
+    pin = pout;
+    pout = (pout == pa) ? pb : pa;
+  }
   return launches;
 }
 
