@@ -452,6 +452,16 @@ stencil_record_kernel(int64_t M, int rank, const int* __restrict__ idx, const F*
   }
 }
 
+// 8 weights of one (point, dimension) as 128-bit stores (the record array is 32-byte aligned per entry)
+__device__ __forceinline__ void store_record8(float* out, const float* w) {
+  reinterpret_cast<float4*>(out)[0] = make_float4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<float4*>(out)[1] = make_float4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void store_record8(double* out, const double* w) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) reinterpret_cast<double2*>(out)[k] = make_double2(w[2 * k], w[2 * k + 1]);
+}
+
 // Fast path of the record kernel for the tile kernels' layout (PX = PY = 8, ns <= 7):
 // one thread per (point, dimension) computes the stencil start once and its 8 weights, and stores
 // them as two 128-bit writes (adjacent threads write adjacent 32-byte chunks: fully coalesced).
@@ -467,11 +477,7 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
   if (skip != nullptr && *skip) return;   // same point set as the last call (opts.reuse_points)
   const int64_t total = M * RANK;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
-    const int64_t j = g / RANK;
-    const int d = static_cast<int>(g - j * RANK);
-    const int i = idx[j];
-    const F x = folded[4 * static_cast<int64_t>(i) + d];
+  auto record = [&](int64_t g, int64_t j, int d, F x) {
     const int i1 = static_cast<int>(ceil(sub_rn(x, half_width)));
     const F x1 = sub_rn(static_cast<F>(i1), x);
     const int shift = ((align >> d) & 1) ? (i1 & 1) : 0;
@@ -486,12 +492,34 @@ stencil_record8_kernel(int64_t M, const int* __restrict__ idx, const F* __restri
 #pragma unroll
     for (int k = 1; k < 7; ++k) w[k] = shift ? e[k - 1] : e[k];
     w[7] = shift ? e[6] : F(0);
-    F* out = wrec + g * 8;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out[k] = w[k];
+    store_record8(wrec + g * 8, w);
     int* st = start + 4 * j;
     if (d == 0) { st[0] = i1 - shift; st[3] = shift; if (RANK < 2) st[1] = 0; if (RANK < 3) st[2] = 0; }
     else st[d] = i1 - shift;
+  };
+  // kInFlight elements per iteration: their coordinates (two dependent, scattered loads each: sorted
+  // index -> folded point) are in flight together; half of this kernel's time was that latency
+  // (cfg3: 0.50 -> 0.35 ms with two in flight).
+  constexpr int kInFlight = 2;   // four: 0.39 ms (56 registers cost resident warps)
+  for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < total; g0 += kInFlight * stride) {
+    int64_t jj[kInFlight];
+    int dd[kInFlight], ii[kInFlight];
+    F xx[kInFlight];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const int64_t g = g0 + u * stride;
+      const bool ok = g < total;
+      jj[u] = ok ? g / RANK : 0;
+      dd[u] = ok ? static_cast<int>(g - jj[u] * RANK) : 0;
+      ii[u] = idx[jj[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) xx[u] = folded[4 * static_cast<int64_t>(ii[u]) + dd[u]];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < total) record(g, jj[u], dd[u], xx[u]);
+    }
   }
 }
 
