@@ -99,15 +99,24 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
                 int* __restrict__ range_flag, const int* __restrict__ skip) {
   if (skip != nullptr && *skip) return;   // same point set as the last call (opts.reuse_points)
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
-    F x[3] = {F(0), F(0), F(0)};
+  struct P3 { F a, b, c; };
+  auto load = [&](int64_t i) {
+    P3 v{F(0), F(0), F(0)};
+    if (i >= M) return v;
     if (layout == 0) {
-      x[0] = p0[i];
-      if (g.rank > 1) x[1] = p1[i];
-      if (g.rank > 2) x[2] = p2[i];
+      v.a = p0[i];
+      if (g.rank > 1) v.b = p1[i];
+      if (g.rank > 2) v.c = p2[i];
     } else {
-      for (int d = 0; d < g.rank; ++d) x[d] = p0[i * g.rank + (g.rank - 1 - d)];
+      const F* q = p0 + i * g.rank + (g.rank - 1);
+      v.a = q[0];
+      if (g.rank > 1) v.b = q[-1];
+      if (g.rank > 2) v.c = q[-2];
     }
+    return v;
+  };
+  auto point = [&](int64_t i, const P3& v) {
+    F x[3] = {v.a, v.b, v.c};
     int bad = 0;
     int key = 0;
     int mul = 1;
@@ -158,6 +167,12 @@ fold_key_kernel(int64_t M, int layout, const F* __restrict__ p0, const F* __rest
     const int leader = __ffs(peers) - 1;
     if ((threadIdx.x & 31) == leader) atomicAdd(&bin_sizes[bin_key], __popc(peers));
     if (bad) atomicOr(range_flag, bad);
+  };
+  // two points per iteration: the second point's coordinates are in flight while the first is folded
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += 2 * stride) {
+    const P3 xa = load(i), xb = load(i + stride);
+    point(i, xa);
+    if (i + stride < M) point(i + stride, xb);
   }
 }
 
