@@ -693,8 +693,12 @@ int do_spread(b200nufft_plan* p, int ntr, const void* c, void* fw, cudaStream_t 
       const int pm = p->opts.reserved[7] == 0 ? 1 : 0;
       const float2* src = cc;
       if (pm) {
-        transpose_strengths_kernel<<<dim3(static_cast<unsigned>((p->M + 31) / 32), (main_n + 31) / 32), dim3(32, 8), 0, st>>>(
-            cc, p->ct.as<float2>(), p->M, main_n);
+        if (p->M % 2 == 0 && reinterpret_cast<uintptr_t>(cc) % 16 == 0)
+          transpose_strengths_wide_kernel<<<dim3(static_cast<unsigned>((p->M + 63) / 64), (main_n + 31) / 32), 256, 0, st>>>(
+              cc, p->ct.as<float2>(), p->M, main_n);
+        else
+          transpose_strengths_kernel<<<dim3(static_cast<unsigned>((p->M + 31) / 32), (main_n + 31) / 32), dim3(32, 8), 0, st>>>(
+              cc, p->ct.as<float2>(), p->M, main_n);
         p->launches++;
         src = p->ct.as<float2>();
       }

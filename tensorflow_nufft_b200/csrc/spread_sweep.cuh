@@ -81,6 +81,45 @@ transpose_strengths_kernel(const float2* __restrict__ c, float2* __restrict__ c_
   }
 }
 
+// The same with 128-bit accesses on both sides: 64 points x 32 coils per CTA, a lane reads two
+// adjacent points of one coil and writes two adjacent coils of one point (needs M even, T even and a
+// 16-byte aligned source). Shared tile [point][coil pair ^ (point / 2 & 7)]: the float4 reads of
+// the write-out are conflict free, the transposing 8-byte stores two-way.
+__global__ void __launch_bounds__(256)
+transpose_strengths_wide_kernel(const float2* __restrict__ c, float2* __restrict__ c_pm, int64_t M, int T) {
+  __shared__ __align__(16) float2 tile[64 * 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int t0 = blockIdx.y * 32;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int t = t0 + (tid >> 5) + 8 * k;
+    const int64_t i = i0 + 2 * lane;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T && i < M) v[k] = *reinterpret_cast<const float4*>(c + static_cast<int64_t>(t) * M + i);   // M even: i + 1 < M
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ty = (tid >> 5) + 8 * k;
+    const int r = 2 * lane;   // rows r, r + 1 share the swizzle (r / 2 & 7)
+    const int col = 2 * ((ty >> 1) ^ (lane & 7)) + (ty & 1);
+    tile[r * 32 + col] = make_float2(v[k].x, v[k].y);
+    tile[(r + 1) * 32 + col] = make_float2(v[k].z, v[k].w);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int iy = (tid >> 4) + 16 * k, q = tid & 15;
+    const int64_t i = i0 + iy;
+    const int t = t0 + 2 * q;
+    if (i < M && t < T) {   // T even: t + 1 < T
+      const float4 w = *reinterpret_cast<const float4*>(&tile[iy * 32 + 2 * (q ^ ((iy >> 1) & 7))]);
+      *reinterpret_cast<float4*>(c_pm + i * T + t) = w;
+    }
+  }
+}
+
 template <int Y>
 inline size_t spread_sweep2d_smem_bytes(const int* bin) {
   const size_t ncell = static_cast<size_t>(bin[0] + kSweepHaloX) * (bin[1] + 8);
