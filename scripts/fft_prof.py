@@ -1,5 +1,7 @@
+"""Scratch for ncu captures of the own FFT passes: one cfg4-shaped type-2 plan (2 x 512^3 fine grid)
+and one cfg2-shaped type-1 plan (32 x 1024^2), few points, two executes each."""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tensorflow_nufft_b200 import _lib
 from tests import helpers as H
