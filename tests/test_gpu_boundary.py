@@ -50,10 +50,14 @@ def test_set_points_and_execute_do_not_allocate_after_reserve():
   plan.close()
 
 
+@pytest.mark.parametrize("pow2", [False, True])
 @pytest.mark.parametrize("ttype,rank", [(1, 2), (2, 2), (2, 3), (1, 3)])
-def test_caller_owned_workspace_matches_plan_owned_buffers(ttype, rank):
+def test_caller_owned_workspace_matches_plan_owned_buffers(ttype, rank, pow2):
   L = _lib()
-  grid = (24, 20) if rank == 2 else (12, 16, 10)
+  if pow2:   # power-of-two fine grids: the engine's own FFT passes (their tables are plan-owned, the grid is not)
+    grid = (32, 64) if rank == 2 else (32, 32, 32)
+  else:
+    grid = (24, 20) if rank == 2 else (12, 16, 10)
   m, T = 7000, 3
   N = int(np.prod(grid))
   pts = torch.from_numpy(H.uniform_points(m, rank, 31)).cuda()
@@ -87,7 +91,7 @@ def test_caller_owned_workspace_matches_plan_owned_buffers(ttype, rank):
   with pytest.raises(L.NufftError):
     plan.execute(out.data_ptr(), src.data_ptr(), torch.cuda.current_stream().cuda_stream)
   plan.close()
-  assert a_created[0] - a0[0] <= 8   # only the small fixed buffers (factors, scan scratch)
+  assert a_created[0] - a0[0] <= (14 if pow2 else 8)   # only the small fixed buffers (factors, FFT tables, scan scratch)
 
 
 def test_allocator_callbacks_own_every_device_buffer():
@@ -106,19 +110,20 @@ def test_allocator_callbacks_own_every_device_buffer():
     torch.cuda.caching_allocator_delete(ptr)
 
   al = L.Allocator(L.ALLOC_FN(alloc), L.FREE_FN(free), None)
-  grid, m = (32, 24), 9000
-  pts = torch.from_numpy(H.uniform_points(m, 2, 41)).cuda()
-  src = torch.from_numpy(H.random_complex((2, 32, 24), 42)).cuda()
-  out = torch.empty((2, m), dtype=torch.complex64, device="cuda")
-  ref = L.Plan(2, grid[::-1], -1, 2, TOL, L.COMPLEX64, device=0)
-  want = _run(ref, pts, src, out, 2)
-  ref.close()
-  plan = L.Plan(2, grid[::-1], -1, 2, TOL, L.COMPLEX64, device=0, allocator=al)
-  got = _run(plan, pts, src, out, 2)
-  assert torch.equal(got, want)
-  assert len(live) >= 10 and sum(live.values()) > m * 64
-  plan.close()
-  assert not live, "plan_destroy must return every buffer to the allocator"
+  for grid in [(32, 24), (32, 64)]:   # cuFFT plan / the engine's own FFT passes (twiddle + factor tables)
+    m = 9000
+    pts = torch.from_numpy(H.uniform_points(m, 2, 41)).cuda()
+    src = torch.from_numpy(H.random_complex((2,) + grid, 42)).cuda()
+    out = torch.empty((2, m), dtype=torch.complex64, device="cuda")
+    ref = L.Plan(2, grid[::-1], -1, 2, TOL, L.COMPLEX64, device=0)
+    want = _run(ref, pts, src, out, 2)
+    ref.close()
+    plan = L.Plan(2, grid[::-1], -1, 2, TOL, L.COMPLEX64, device=0, allocator=al)
+    got = _run(plan, pts, src, out, 2)
+    assert torch.equal(got, want)
+    assert len(live) >= 10 and sum(live.values()) > m * 64
+    plan.close()
+    assert not live, "plan_destroy must return every buffer to the allocator"
 
 
 def test_plan_cache_hands_out_idle_plans_only_and_evicts_lru():
