@@ -196,12 +196,13 @@ def test_user_batch_size_is_clamped_to_the_grid_limit():
   plan.close()
 
 
+@pytest.mark.parametrize("grid", [(64, 48), (256, 256)])   # cuFFT plan / the engine's own FFT passes (64 KB bundles)
 @pytest.mark.parametrize("ttype", [1, 2])
-def test_set_points_and_execute_capture_into_a_cuda_graph(ttype):
+def test_set_points_and_execute_capture_into_a_cuda_graph(ttype, grid):
   """No allocation, no host synchronisation, no cross-stream events on the hot path: the pair is
   capturable and the replayed graph gives the same result on new input data."""
   L = _lib()
-  grid, m, T = (64, 48), 20000, 2
+  m, T = 20000, 2
   N = grid[0] * grid[1]
   pts = torch.from_numpy(H.uniform_points(m, 2, 61)).cuda()
   src = torch.from_numpy(H.random_complex((T, m) if ttype == 1 else (T, N), 62)).cuda()
