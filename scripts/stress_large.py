@@ -27,4 +27,10 @@ check("3d-192-30M", (192, 192, 192), 30_000_000, 1, 2)
 check("2d-4096-8M-T3", (4096, 4096), 8_000_000, 3, 3)
 check("3d-320-6M", (320, 320, 320), 6_000_000, 1, 4)
 check("2d-32-20M-dense", (32, 32), 20_000_000, 8, 5)
+# power-of-two fine grids: the engine's own FFT passes at their largest sizes (nf = 1024 per axis:
+# 8-column bundles, 64-bit strides) and with batches
+check("3d-512-10M-ownfft", (512, 512, 512), 10_000_000, 1, 6)
+check("2d-512-4M-T40-ownfft", (512, 512), 4_000_000, 40, 7)
+check("3d-256-4M-T3-ownfft", (256, 256, 256), 4_000_000, 3, 8)
+check("3d-mixed-ownfft", (32, 512, 128), 3_000_000, 2, 9)
 print("stress_large: ok")
